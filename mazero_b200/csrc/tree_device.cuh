@@ -1,0 +1,405 @@
+// tree_device.cuh -- device-side building blocks of the sampled-MCTS tree engine (sm_100a).
+//
+// Execution model: ONE WARP OWNS ONE TREE for the whole kernel.  No atomics, no cross-warp sharing.
+// Lanes are used for (a) the children of the node being scored / created, (b) the (sample k, agent i)
+// pairs of the joint-action draw, (c) scanning the tree's value log, (d) the 624-word mt19937 twist.
+//
+// Bit-exactness: every fp32/fp64 operation that the reference performs is issued here with an explicit
+// round-to-nearest intrinsic (__fmul_rn/__fadd_rn/__ddiv_rn ...) so that nvcc cannot contract a*b+c
+// into an FMA (the reference is built for baseline x86-64: no FMA; core/mcts/ctree/setup.py:34).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tree_layout.h"
+
+namespace maz {
+
+#define MAZ_FULL 0xffffffffu
+
+// ---- slab field accessors --------------------------------------------------------------------------
+#define MAZ_FIELD(type, name, off)                                                                      \
+    __device__ __forceinline__ type *name(const TreeLayout &L, char *tb) { return reinterpret_cast<type *>(tb + L.off); }
+MAZ_FIELD(uint32_t, f_mt, off_mt)
+MAZ_FIELD(float, f_prior, off_prior)
+MAZ_FIELD(float, f_pred_prob, off_pred_prob)
+MAZ_FIELD(float, f_beta, off_beta)
+MAZ_FIELD(float, f_beta_hat, off_beta_hat)
+MAZ_FIELD(float, f_reward, off_reward)
+MAZ_FIELD(float, f_pred_value, off_pred_value)
+MAZ_FIELD(float, f_wsum, off_wsum)
+MAZ_FIELD(float, f_wtot, off_wtot)
+MAZ_FIELD(float, f_qdelta, off_qdelta)
+MAZ_FIELD(int, f_visit, off_visit)
+MAZ_FIELD(uint16_t, f_nchild, off_nchild)
+MAZ_FIELD(uint16_t, f_cbase, off_cbase)
+MAZ_FIELD(int16_t, f_hidx, off_hidx)
+MAZ_FIELD(uint8_t, f_actions, off_actions)
+MAZ_FIELD(uint16_t, f_expslot, off_expslot)
+MAZ_FIELD(uint16_t, f_path, off_path)
+MAZ_FIELD(uint32_t, f_vskey, off_vskey)
+MAZ_FIELD(float, f_vsval, off_vsval)
+#undef MAZ_FIELD
+
+__device__ __forceinline__ TreeHdr *f_hdr(char *tb) { return reinterpret_cast<TreeHdr *>(tb); }
+
+// order-preserving float <-> uint map (for redux.sync min/max on floats)
+__device__ __forceinline__ uint32_t f2ord(float f)
+{
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u)
+{
+    uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(b);
+}
+
+// ---- std::mt19937 -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mt_temper(uint32_t z)
+{
+    z ^= z >> 11;
+    z ^= (z << 7) & 0x9d2c5680u;
+    z ^= (z << 15) & 0xefc60000u;
+    z ^= z >> 18;
+    return z;
+}
+
+// Regenerate the 624-word block in registers: lane l holds words 32c+l (c = 0..19).  Word i needs
+// word i+1 (old) and word i+397 (old, i < 227) or i-227 (new, i >= 227): all reachable with shuffles
+// whose source REGISTER index is a compile-time constant once the c-loop is unrolled.
+__device__ __forceinline__ void mt_regen(uint32_t *s, int lane)
+{
+    uint32_t r[20];
+#pragma unroll
+    for (int c = 0; c < 20; ++c) {
+        int i = c * 32 + lane;
+        r[c] = (i < kMtN) ? s[i] : 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < 20; ++c) {
+        const int i = c * 32 + lane;
+        // s[i+1]: same register one lane up, or lane 0 of the next register; i = 623 wraps to the NEW s[0]
+        uint32_t nxt = __shfl_down_sync(MAZ_FULL, r[c], 1);
+        uint32_t nxt_next = __shfl_sync(MAZ_FULL, r[(c < 19) ? c + 1 : 0], 0);
+        if (lane == 31 || (c == 19 && lane == 15)) nxt = nxt_next;
+        // s[i+397] = register c+12 (+1 when lane+13 wraps), lane (lane+13)&31      [i < 227]
+        // s[i-227] = register c-8  (+1 when lane+29 wraps), lane (lane+29)&31      [i >= 227]
+        uint32_t src = 0;
+        if (c <= 7) {
+            uint32_t a_lo = __shfl_sync(MAZ_FULL, r[(c + 12 <= 19) ? c + 12 : 19], (lane + 13) & 31);
+            uint32_t a_hi = __shfl_sync(MAZ_FULL, r[(c + 13 <= 19) ? c + 13 : 19], (lane + 13) & 31);
+            src = (lane < 19) ? a_lo : a_hi;
+        }
+        if (c >= 7) {
+            uint32_t b_lo = __shfl_sync(MAZ_FULL, r[(c >= 8) ? c - 8 : 0], (lane + 29) & 31);
+            uint32_t b_hi = __shfl_sync(MAZ_FULL, r[c - 7], (lane + 29) & 31);
+            uint32_t b = (lane < 3) ? b_lo : b_hi;
+            if (i >= 227) src = b;
+        }
+        uint32_t y = (r[c] & 0x80000000u) | (nxt & 0x7fffffffu);
+        uint32_t v = src ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        if (i < kMtN) r[c] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < 20; ++c) {
+        int i = c * 32 + lane;
+        if (i < kMtN) s[i] = r[c];
+    }
+}
+
+// Stage the next n (<= kMtChunk) tempered outputs of the tree's generator into out[] (shared memory).
+// mt_pos is the warp-uniform stream position (kept in a register by the caller).
+__device__ __forceinline__ void mt_fetch(uint32_t *s, int &mt_pos, uint32_t *out, int n, int lane)
+{
+    const int p = mt_pos;
+    for (int t = lane; t < n; t += 32) {
+        int q = p + t;
+        if (q < kMtN) out[t] = mt_temper(s[q]);
+    }
+    if (p + n > kMtN) {
+        __syncwarp();
+        mt_regen(s, lane);
+        __syncwarp();
+        for (int t = lane; t < n; t += 32) {
+            int q = p + t;
+            if (q >= kMtN) out[t] = mt_temper(s[q - kMtN]);
+        }
+        mt_pos = p + n - kMtN;
+    } else {
+        mt_pos = p + n;
+    }
+    __syncwarp();
+}
+
+// One raw draw (std::mt19937::operator()), warp-uniform result.
+__device__ __forceinline__ uint32_t mt_next(uint32_t *s, int &mt_pos, int lane)
+{
+    if (mt_pos >= kMtN) {
+        __syncwarp();
+        mt_regen(s, lane);
+        __syncwarp();
+        mt_pos = 0;
+    }
+    uint32_t z = mt_temper(s[mt_pos]);  // same address in every lane: one broadcast transaction
+    mt_pos += 1;
+    return z;
+}
+
+// std::generate_canonical<double,53>(mt19937) from two consecutive 32-bit draws (random.tcc:3362-3378)
+__device__ __forceinline__ double mt_canonical(uint32_t x1, uint32_t x2)
+{
+    double sum = __dadd_rn((double)x1, __dmul_rn((double)x2, 4294967296.0));
+    double r = __dmul_rn(sum, 5.42101086242752217e-20);  // exact: * 2^-64
+    if (r >= 1.0) r = 0.99999999999999988897769753748;   // nextafter(1.0, 0.0)
+    return r;
+}
+
+// ---- per-warp shared-memory scratch of the expansion ----------------------------------------------
+struct ExpandScratch {
+    double *cp;         // [N*A] cumulative probabilities (std::discrete_distribution::_M_cp)
+    long long *keys;    // [32]
+    float *beta;        // [N*A]
+    uint32_t *draws;    // [kMtChunk]
+    uint8_t *samp;      // [K*N] sampled per-agent actions
+};
+__host__ __device__ inline size_t expand_scratch_bytes(int N, int A, int K)
+{
+    size_t na = (size_t)N * A;
+    size_t b = 8 * na + 8 * 32 + 4 * na + 4 * kMtChunk + (size_t)K * N;
+    return (b + 15) & ~(size_t)15;
+}
+__device__ __forceinline__ ExpandScratch carve_scratch(char *p, int N, int A)
+{
+    ExpandScratch s;
+    size_t na = (size_t)N * A;
+    s.cp = reinterpret_cast<double *>(p);
+    s.keys = reinterpret_cast<long long *>(p + 8 * na);
+    s.beta = reinterpret_cast<float *>(p + 8 * na + 256);
+    s.draws = reinterpret_cast<uint32_t *>(p + 8 * na + 256 + 4 * na);
+    s.samp = reinterpret_cast<uint8_t *>(p + 8 * na + 256 + 4 * na + 4 * kMtChunk);
+    return s;
+}
+
+// ---- CTree::expand (cnode.cpp:224-295) --------------------------------------------------------------
+// Samples K joint actions from the factorised per-agent distribution beta, merges duplicates, creates
+// the children in ascending (wrapped, signed 64-bit) key order in consecutive slots.  Returns the number
+// of children.  `probs`, `beta`, `noises` point at this tree's (N,A) rows in global memory.
+__device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &tot_nodes, int &n_expanded, int &mt_pos,
+                                           int &err, int slot, int hidx, float reward, float value,
+                                           const float *__restrict__ probs, const float *__restrict__ beta,
+                                           int K, float eps, const float *__restrict__ noises,
+                                           const ExpandScratch &sc, int lane)
+{
+    const int N = L.N, A = L.A, NA = N * A;
+
+    for (int t = lane; t < NA; t += 32) sc.beta[t] = beta[t];
+    __syncwarp();
+
+    if (A >= 2) {
+        // std::discrete_distribution::param_type::_M_initialize (random.tcc:2657-2678): sequential fp64
+        for (int i = lane; i < N; i += 32) {
+            const float *bi = sc.beta + i * A;
+            double sum = 0.0;
+            for (int a = 0; a < A; ++a) sum = __dadd_rn(sum, (double)bi[a]);
+            double run = 0.0;
+            for (int a = 0; a < A; ++a) {
+                double p = __ddiv_rn((double)bi[a], sum);
+                run = (a == 0) ? p : __dadd_rn(run, p);
+                sc.cp[i * A + a] = run;
+            }
+            sc.cp[i * A + A - 1] = 1.0;
+        }
+        __syncwarp();
+        // K*N draws in (k major, agent minor) order (cnode.cpp:251-259); 2 raw outputs per draw
+        const int KN = K * N;
+        uint32_t *mt = f_mt(L, tb);
+        for (int j0 = 0; j0 < KN; j0 += kMtChunk / 2) {
+            const int np = min(kMtChunk / 2, KN - j0);
+            mt_fetch(mt, mt_pos, sc.draws, 2 * np, lane);
+            for (int t = lane; t < np; t += 32) {
+                const int j = j0 + t;
+                const int i = j % N;
+                const double u = mt_canonical(sc.draws[2 * t], sc.draws[2 * t + 1]);
+                const double *c = sc.cp + i * A;
+                int lo = 0, hi = A;  // std::lower_bound: first c[a] with !(c[a] < u)
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (c[mid] < u) lo = mid + 1; else hi = mid;
+                }
+                sc.samp[j] = (uint8_t)lo;
+            }
+            __syncwarp();
+        }
+    } else {
+        // A < 2: empty _M_cp, operator() returns 0 and consumes no randomness (random.tcc:2696-2697)
+        for (int t = lane; t < K * N; t += 32) sc.samp[t] = 0;
+        __syncwarp();
+    }
+
+    // hash key of sample k = lane (cnode.cpp:258): key = key*23333 + a, C `long` wrap-around
+    unsigned long long ukey = 0;
+    if (lane < K) {
+        const uint8_t *sk = sc.samp + lane * N;
+        for (int i = 0; i < N; ++i) ukey = ukey * 23333ull + (unsigned long long)sk[i];
+        sc.keys[lane] = (long long)ukey;
+    }
+    __syncwarp();
+    const long long key = (long long)ukey;
+    // std::map semantics: count per distinct key, action vector of the LAST sample with that key,
+    // children in ascending key order.
+    int cnt = 0;
+    bool is_last = lane < K;
+    for (int j = 0; j < K; ++j) {
+        long long kj = sc.keys[j];
+        if (lane < K && kj == key) {
+            ++cnt;
+            if (j > lane) is_last = false;
+        }
+    }
+    const unsigned lastmask = __ballot_sync(MAZ_FULL, is_last);
+    int rank = 0;
+    for (int j = 0; j < K; ++j) {
+        long long kj = sc.keys[j];
+        if (((lastmask >> j) & 1u) && kj < key) ++rank;
+    }
+    const int C = __popc(lastmask);
+    const int base = tot_nodes;
+    if (base + C > L.P) {
+        err = kErrPoolExhausted;
+        return 0;
+    }
+
+    if (is_last) {
+        const uint8_t *sk = sc.samp + lane * N;
+        const int cs = base + rank;
+        const float betahat_prob = __fdiv_rn((float)cnt, (float)K);  // count / sampled_times
+        float beta_prob = 1.0f, pred_prob = 1.0f, prior = 1.0f;
+        const float ome = __fsub_rn(1.0f, eps);
+        uint8_t *act = f_actions(L, tb) + (size_t)cs * N;
+        for (int i = 0; i < N; ++i) {
+            const int a = sk[i];
+            const float pb = sc.beta[i * A + a];
+            const float pp = __ldg(probs + i * A + a);
+            beta_prob = __fmul_rn(beta_prob, pb);
+            pred_prob = __fmul_rn(pred_prob, pp);
+            if (eps > 0) {
+                float p = __fadd_rn(__fmul_rn(pp, ome), __fmul_rn(__ldg(noises + i * A + a), eps));
+                prior = __fmul_rn(prior, p);
+            } else {
+                prior = __fmul_rn(prior, pp);
+            }
+            act[i] = (uint8_t)a;
+        }
+        prior = __fdiv_rn(__fmul_rn(prior, betahat_prob), beta_prob);
+        f_prior(L, tb)[cs] = prior;
+        f_pred_prob(L, tb)[cs] = pred_prob;
+        f_beta(L, tb)[cs] = beta_prob;
+        f_beta_hat(L, tb)[cs] = betahat_prob;
+        f_visit(L, tb)[cs] = 0;
+        f_nchild(L, tb)[cs] = 0;
+        f_hidx(L, tb)[cs] = -1;
+        f_reward(L, tb)[cs] = 0.0f;      // CNode ctor: reward(0.), pred_value(0.)  (cnode.cpp:14-16);
+        f_pred_value(L, tb)[cs] = 0.0f;  // the root readouts return these for never-expanded children
+    }
+    if (lane == 0) {
+        f_hidx(L, tb)[slot] = (int16_t)hidx;
+        f_reward(L, tb)[slot] = reward;
+        f_pred_value(L, tb)[slot] = value;
+        f_nchild(L, tb)[slot] = (uint16_t)C;
+        f_cbase(L, tb)[slot] = (uint16_t)base;
+        f_wsum(L, tb)[slot] = 0.0f;
+        f_wtot(L, tb)[slot] = 0.0f;
+        f_expslot(L, tb)[n_expanded] = (uint16_t)slot;
+    }
+    tot_nodes = base + C;
+    n_expanded += 1;
+    __syncwarp();
+    return C;
+}
+
+// ---- SubTreeValueSet::update (utils.cpp:20-71) on the per-tree value log -----------------------------
+// wsum / wtot are the node's weighted_sum / tot_weight (warp-uniform registers, written back by caller).
+__device__ __forceinline__ void vs_update(const TreeLayout &L, char *tb, int &log_len, int &err, float &wsum, float &wtot,
+                                          int slot, int depth, float key, const float *__restrict__ lam_pow, int lane)
+{
+    uint32_t *vk = f_vskey(L, tb);
+    float *vv = f_vsval(L, tb);
+    const uint32_t tag = ((uint32_t)slot << 16) | ((uint32_t)depth << 1);
+    int cnt = 0, nbig = 0;
+    uint32_t minbig = 0xffffffffu, maxsmall = 0u;
+    int minpos = -1, maxpos = -1;
+    for (int e = lane; e < log_len; e += 32) {
+        const uint32_t k = vk[e];
+        const float v = vv[e];
+        if ((k & ~1u) == tag) {
+            const uint32_t o = f2ord(v);
+            ++cnt;
+            if (k & 1u) {
+                ++nbig;
+                if (o < minbig || minpos < 0) { minbig = o; minpos = e; }
+            } else {
+                if (o > maxsmall || maxpos < 0) { maxsmall = o; maxpos = e; }
+            }
+        }
+    }
+    cnt = __reduce_add_sync(MAZ_FULL, cnt);
+    nbig = __reduce_add_sync(MAZ_FULL, nbig);
+    const int nsmall = cnt - nbig;
+    const float lp = lam_pow[depth];
+    // size_lim = max(1, (int)ceil(count * (1 - quantile)))  (utils.cpp:31; float product, ceil)
+    int lim = __float2int_ru(__fmul_rn((float)(cnt + 1), L.one_minus_rho));
+    if (lim < 1) lim = 1;
+
+    bool append_big;
+    int flip_pos = -1;       // log entry whose big/small flag flips
+    if (nbig == lim) {       // utils.cpp:33-48
+        const uint32_t gmin = __reduce_min_sync(MAZ_FULL, minpos >= 0 ? minbig : 0xffffffffu);
+        const float m = ord2f(gmin);
+        if (key < m) {
+            append_big = false;
+        } else {
+            const unsigned who = __ballot_sync(MAZ_FULL, minpos >= 0 && minbig == gmin);
+            flip_pos = __shfl_sync(MAZ_FULL, minpos, __ffs(who) - 1);
+            wsum = __fsub_rn(wsum, __fmul_rn(lp, m));
+            wtot = __fsub_rn(wtot, lp);
+            append_big = true;
+            wtot = __fadd_rn(wtot, lp);
+            wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
+        }
+    } else {                 // utils.cpp:49-70
+        if (nbig + 1 != lim) err = kErrValueSetInvariant;
+        if (nsmall == 0) {
+            append_big = true;
+            wtot = __fadd_rn(wtot, lp);
+            wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
+        } else {
+            const uint32_t gmax = __reduce_max_sync(MAZ_FULL, maxpos >= 0 ? maxsmall : 0u);
+            const float M = ord2f(gmax);
+            if (key > M) {
+                append_big = true;
+                wtot = __fadd_rn(wtot, lp);
+                wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
+            } else {
+                const unsigned who = __ballot_sync(MAZ_FULL, maxpos >= 0 && maxsmall == gmax);
+                flip_pos = __shfl_sync(MAZ_FULL, maxpos, __ffs(who) - 1);
+                wtot = __fadd_rn(wtot, lp);
+                wsum = __fadd_rn(wsum, __fmul_rn(lp, M));
+                append_big = false;
+            }
+        }
+    }
+    if (log_len >= L.L) {
+        err = kErrLogOverflow;
+        return;
+    }
+    if (lane == 0) {
+        if (flip_pos >= 0) vk[flip_pos] ^= 1u;
+        vk[log_len] = tag | (append_big ? 1u : 0u);
+        vv[log_len] = key;
+    }
+    log_len += 1;
+    __syncwarp();
+}
+
+}  // namespace maz

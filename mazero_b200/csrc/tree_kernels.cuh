@@ -1,0 +1,344 @@
+// tree_kernels.cuh -- the sm_100a kernels of the batched sampled-MCTS tree engine.
+// One warp per tree; blockDim.x = 32 * warps_per_block; trees are independent (no atomics).
+#pragma once
+#include "tree_device.cuh"
+
+namespace maz {
+
+__device__ __forceinline__ bool warp_tree(const TreeLayout &L, int &tree, int &lane)
+{
+    tree = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    lane = threadIdx.x & 31;
+    return tree < L.B;
+}
+
+// ---- std::mt19937(seed) for every tree (cnode.cpp:574, 186-189): one thread per tree ----------------
+__global__ void k_seed(TreeLayout L, char *arena, unsigned int seed_base)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.B) return;
+    char *tb = arena + (size_t)b * L.slab_bytes;
+    uint32_t *s = f_mt(L, tb);
+    uint32_t x = seed_base + (unsigned int)b;
+    s[0] = x;
+    for (int i = 1; i < kMtN; ++i) {
+        x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
+        s[i] = x;
+    }
+    TreeHdr *h = f_hdr(tb);
+    h->mt_pos = kMtN;
+    h->err = 0;
+}
+
+// ---- CTree_batch::prepare -> CTree::prepare (cnode.cpp:589-614, 205-222) ------------------------------
+__global__ void k_prepare(TreeLayout L, char *arena, const float *__restrict__ lam_pow,
+                          const float *__restrict__ rewards, const float *__restrict__ values,
+                          const float *__restrict__ probs, const float *__restrict__ beta, int K, float eps,
+                          const float *__restrict__ noises, int *g_err)
+{
+    extern __shared__ __align__(16) char smem[];
+    int tree, lane;
+    if (!warp_tree(L, tree, lane)) return;
+    char *tb = arena + (size_t)tree * L.slab_bytes;
+    TreeHdr *h = f_hdr(tb);
+    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+
+    int tot_nodes = 1, n_expanded = 0, log_len = 0, err = 0;
+    int mt_pos = h->mt_pos;
+    if (lane == 0) {  // new (root) CNode(1,1,1,1,true,...)  cnode.cpp:217
+        f_prior(L, tb)[0] = 1.0f;
+        f_pred_prob(L, tb)[0] = 1.0f;
+        f_beta(L, tb)[0] = 1.0f;
+        f_beta_hat(L, tb)[0] = 1.0f;
+        f_visit(L, tb)[0] = 0;
+        f_qdelta(L, tb)[0] = 0.0f;
+    }
+    const size_t NA = (size_t)L.N * L.A;
+    const float value = values[tree];
+    expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, 0, 0, rewards[tree], value, probs + tree * NA,
+                beta + tree * NA, K, eps, noises + tree * NA, sc, lane);
+    float ws = 0.0f, wt = 0.0f;
+    vs_update(L, tb, log_len, err, ws, wt, 0, 0, value, lam_pow, lane);  // root.subtree_info.update(value, 0)
+    if (lane == 0) {
+        f_visit(L, tb)[0] = 1;
+        f_wsum(L, tb)[0] = ws;
+        f_wtot(L, tb)[0] = wt;
+        h->tot_nodes = tot_nodes;
+        h->log_len = log_len;
+        h->path_len = 0;
+        h->mt_pos = mt_pos;
+        h->mm_min = 0.0f;
+        h->mm_max = 0.0f;
+        h->mm_cnt = 0;
+        h->n_expanded = n_expanded;
+        h->err = err;
+        h->sum_path_len = 0;
+        if (err) *g_err = err;
+    }
+}
+
+// ---- CTree_batch::cbatch_selection -> CTree::select_path / select_child / ucb_score --------------------
+// (cnode.cpp:616-642, 381-413, 337-379, 297-335)
+__global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ logterm, const double *__restrict__ sqrtn,
+                         int table_len, float discount, int *__restrict__ idx_x, int *__restrict__ idx_y,
+                         int *__restrict__ act_out, int *g_err)
+{
+    int tree, lane;
+    if (!warp_tree(L, tree, lane)) return;
+    char *tb = arena + (size_t)tree * L.slab_bytes;
+    TreeHdr *h = f_hdr(tb);
+    int mt_pos = h->mt_pos;
+    const float mn = h->mm_min, mx = h->mm_max;
+    const int mmc = h->mm_cnt;
+    uint16_t *path = f_path(L, tb);
+    const uint16_t *nchild = f_nchild(L, tb);
+    const uint16_t *cbase = f_cbase(L, tb);
+    const int *visit = f_visit(L, tb);
+    const float *pred_value = f_pred_value(L, tb);
+    uint32_t *mt = f_mt(L, tb);
+
+    int node = 0, parent = 0, len = 0, err = 0;
+    if (lane == 0) path[0] = 0;
+    while (true) {
+        const int C = nchild[node];
+        if (C == 0) break;
+        const int base = cbase[node];
+        const int vc = visit[node];
+        int ci;
+        if (node == 0 && vc <= C) {
+            ci = vc - 1;  // forced root round-robin, no RNG draw (cnode.cpp:398-399)
+        } else {
+            const float pq = pred_value[node];
+            int n = vc - 1;
+            if (n >= table_len) n = table_len - 1;
+            float score = 0.0f;
+            if (lane < C) {
+                const int cs = base + lane;
+                const float prior = f_prior(L, tb)[cs];
+                const int cvis = visit[cs];
+                const float rew = f_reward(L, tb)[cs];
+                const float ws = f_wsum(L, tb)[cs];
+                const float wt = f_wtot(L, tb)[cs];
+                // pb_c = log((n + c_base + 1)/c_base) + c_init   [float <- double]   (host table)
+                // pb_c *= sqrt(n) / (visit + 1)                   [float <- double product]
+                const float pb_c = (float)__dmul_rn((double)logterm[n], __ddiv_rn(sqrtn[n], (double)(cvis + 1)));
+                const float prior_score = __fmul_rn(pb_c, prior);
+                float v = 0.0f;
+                if (cvis != 0) v = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), pq);
+                if (mmc > 0) {  // CMinMaxStats::normalize (utils.cpp:95-103)
+                    const float delta = __fsub_rn(mx, mn);
+                    const float den = (L.delta_lb < delta) ? delta : L.delta_lb;
+                    v = __fdiv_rn(__fsub_rn(v, mn), den);
+                }
+                if (v < 0.0f) v = 0.0f;
+                if (v > 1.0f) v = 1.0f;
+                score = __fadd_rn(prior_score, v);
+            }
+            // sequential epsilon-tie list of cnode.cpp:351-370, evaluated in parallel:
+            // list = {first index of the maximum} U {later indices with score >= max - 1e-6f}
+            const bool valid = (lane < C) && (score > -1000000.0f);
+            const uint32_t o = valid ? f2ord(__fadd_rn(score, 0.0f)) : 0u;
+            const uint32_t gmax = __reduce_max_sync(MAZ_FULL, o);
+            const unsigned anyvalid = __ballot_sync(MAZ_FULL, valid);
+            unsigned listmask;
+            if (anyvalid) {
+                const float M = ord2f(gmax);
+                const unsigned ismax = __ballot_sync(MAZ_FULL, valid && score == M);
+                const int istar = __ffs(ismax) - 1;
+                const float thr = __fsub_rn(M, 0.000001f);
+                listmask = __ballot_sync(MAZ_FULL, (lane < C) && (lane > istar) && (score >= thr)) | (1u << istar);
+            } else {
+                const float thr = __fsub_rn(-1000000.0f, 0.000001f);
+                listmask = __ballot_sync(MAZ_FULL, (lane < C) && (score >= thr));
+            }
+            const int nl = __popc(listmask);
+            ci = 0;
+            if (nl > 0) {  // one raw draw even for a single candidate (cnode.cpp:373-377)
+                const uint32_t r = mt_next(mt, mt_pos, lane);
+                ci = (int)__fns(listmask, 0, (int)(r % (uint32_t)nl) + 1);
+            }
+        }
+        parent = node;
+        node = base + ci;
+        ++len;
+        if (len > L.S + 1) {
+            err = kErrPathOverflow;
+            break;
+        }
+        if (lane == 0) path[len] = (uint16_t)node;
+    }
+    if (lane == 0) {
+        h->path_len = len;
+        h->mt_pos = mt_pos;
+        h->sum_path_len += len;
+        idx_x[tree] = f_hidx(L, tb)[parent];
+        idx_y[tree] = tree;
+        if (err) {
+            h->err = err;
+            *g_err = err;
+        }
+    }
+    const uint8_t *act = f_actions(L, tb) + (size_t)node * L.N;
+    for (int j = lane; j < L.N; j += 32) act_out[(size_t)tree * L.N + j] = act[j];
+}
+
+// ---- CTree_batch::cbatch_expansion_and_backup -> expand_and_backprop / back_propagate ------------------
+// (cnode.cpp:644-670, 452-469, 415-450)
+__global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restrict__ lam_pow, int hidx, float discount,
+                                int K, const float *__restrict__ rewards, const float *__restrict__ values,
+                                const float *__restrict__ probs, const float *__restrict__ beta, int *g_err)
+{
+    extern __shared__ __align__(16) char smem[];
+    int tree, lane;
+    if (!warp_tree(L, tree, lane)) return;
+    char *tb = arena + (size_t)tree * L.slab_bytes;
+    TreeHdr *h = f_hdr(tb);
+    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+
+    int tot_nodes = h->tot_nodes, log_len = h->log_len, mt_pos = h->mt_pos, n_expanded = h->n_expanded, err = h->err;
+    const int len = h->path_len;
+    const uint16_t *path = f_path(L, tb);
+    const int leaf = path[len];
+    const size_t NA = (size_t)L.N * L.A;
+    const float value = values[tree];
+
+    expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, rewards[tree], value, probs + tree * NA,
+                beta + tree * NA, K, 0.0f, nullptr, sc, lane);
+
+    float *reward = f_reward(L, tb), *wsum = f_wsum(L, tb), *wtot = f_wtot(L, tb);
+    float G = value;
+    for (int i = len; i >= 0; --i) {
+        const int slot = path[i];
+        const float rew = reward[slot];
+        float ws = wsum[slot], wt = wtot[slot];
+        // (the reference removes the node's old q-delta from the min-max multiset here; in this layout
+        //  the entry simply lives in qdelta[slot] and is overwritten below)
+        vs_update(L, tb, log_len, err, ws, wt, slot, len - i, G, lam_pow, lane);
+        if (lane == 0) {
+            f_visit(L, tb)[slot] += 1;
+            wsum[slot] = ws;
+            wtot[slot] = wt;
+            if (i != 0) {
+                const float pv = f_pred_value(L, tb)[path[i - 1]];
+                f_qdelta(L, tb)[slot] = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), pv);
+            }
+        }
+        G = __fadd_rn(rew, __fmul_rn(discount, G));
+    }
+    __syncwarp();
+    // CMinMaxStats min / max = reduction over the q-deltas of all visited (= expanded) non-root nodes
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    const uint16_t *expslot = f_expslot(L, tb);
+    const float *qdelta = f_qdelta(L, tb);
+    for (int e = 1 + lane; e < n_expanded; e += 32) {
+        const uint32_t o = f2ord(qdelta[expslot[e]]);
+        lo = min(lo, o);
+        hi = max(hi, o);
+    }
+    lo = __reduce_min_sync(MAZ_FULL, lo);
+    hi = __reduce_max_sync(MAZ_FULL, hi);
+    if (lane == 0) {
+        h->tot_nodes = tot_nodes;
+        h->log_len = log_len;
+        h->mt_pos = mt_pos;
+        h->n_expanded = n_expanded;
+        h->mm_cnt = n_expanded - 1;
+        h->mm_min = ord2f(lo);
+        h->mm_max = ord2f(hi);
+        h->err = err;
+        if (err) *g_err = err;
+    }
+}
+
+// ---- readouts (cnode.cpp:69-171, 471-530, 672-781) ------------------------------------------------------
+struct ReadoutPtrs {
+    float *values;
+    int *marg_visits;
+    float *marg_priors;
+    int *num_children;
+    int *actions;
+    int *visits;
+    float *pred_probs, *beta, *beta_hat, *priors, *imp_ratio, *pred_values, *mcts_values, *rewards, *qvalues;
+};
+
+__global__ void k_readout(TreeLayout L, char *arena, float discount, ReadoutPtrs o)
+{
+    int tree, lane;
+    if (!warp_tree(L, tree, lane)) return;
+    char *tb = arena + (size_t)tree * L.slab_bytes;
+    const int C = f_nchild(L, tb)[0];
+    const int base = f_cbase(L, tb)[0];
+    const int K = L.K, N = L.N, A = L.A;
+    if (lane == 0) {
+        if (o.values) o.values[tree] = __fdiv_rn(f_wsum(L, tb)[0], f_wtot(L, tb)[0]);
+        if (o.num_children) o.num_children[tree] = C;
+    }
+    int cvis = 0;
+    float prior = 0.0f;
+    if (lane < K) {
+        const size_t oi = (size_t)tree * K + lane;
+        float pp = 0, b = 0, bh = 0, imp = 0, pv = 0, mv = 0, rew = 0, q = 0;
+        if (lane < C) {
+            const int cs = base + lane;
+            prior = f_prior(L, tb)[cs];
+            cvis = f_visit(L, tb)[cs];
+            pp = f_pred_prob(L, tb)[cs];
+            b = f_beta(L, tb)[cs];
+            bh = f_beta_hat(L, tb)[cs];
+            imp = __fmul_rn(__fdiv_rn(bh, b), pp);
+            pv = f_pred_value(L, tb)[cs];
+            rew = f_reward(L, tb)[cs];
+            if (f_nchild(L, tb)[cs] > 0) mv = __fdiv_rn(f_wsum(L, tb)[cs], f_wtot(L, tb)[cs]);
+            q = __fadd_rn(rew, __fmul_rn(discount, mv));
+        }
+        if (o.visits) o.visits[oi] = cvis;
+        if (o.pred_probs) o.pred_probs[oi] = pp;
+        if (o.beta) o.beta[oi] = b;
+        if (o.beta_hat) o.beta_hat[oi] = bh;
+        if (o.priors) o.priors[oi] = prior;
+        if (o.imp_ratio) o.imp_ratio[oi] = imp;
+        if (o.pred_values) o.pred_values[oi] = pv;
+        if (o.mcts_values) o.mcts_values[oi] = mv;
+        if (o.rewards) o.rewards[oi] = rew;
+        if (o.qvalues) o.qvalues[oi] = q;
+    }
+    const uint8_t *act = f_actions(L, tb) + (size_t)base * N;
+    if (o.actions) {
+        for (int t = lane; t < K * N; t += 32) o.actions[(size_t)tree * K * N + t] = (t < C * N) ? (int)act[t] : 0;
+    }
+    if (o.marg_visits || o.marg_priors) {
+        // scatter-add over root children in child order (float adds in that order, cnode.cpp:81-91)
+        for (int t0 = 0; t0 < N * A; t0 += 32) {
+            const int t = t0 + lane;
+            const int j = t / A, a = t - j * A;
+            int iv = 0;
+            float fp = 0.0f;
+            for (int c = 0; c < C; ++c) {
+                const int vcc = __shfl_sync(MAZ_FULL, cvis, c);
+                const float prc = __shfl_sync(MAZ_FULL, prior, c);
+                if (t < N * A && act[(size_t)c * N + j] == a) {
+                    iv += vcc;
+                    fp = __fadd_rn(fp, prc);
+                }
+            }
+            if (t < N * A) {
+                if (o.marg_visits) o.marg_visits[(size_t)tree * N * A + t] = iv;
+                if (o.marg_priors) o.marg_priors[(size_t)tree * N * A + t] = fp;
+            }
+        }
+    }
+}
+
+// ---- statistics ------------------------------------------------------------------------------------------
+__global__ void k_stats(TreeLayout L, char *arena, int *tot_nodes, int *last_len, unsigned long long *sums)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.B) return;
+    const TreeHdr *h = f_hdr(arena + (size_t)b * L.slab_bytes);
+    if (tot_nodes) tot_nodes[b] = h->tot_nodes;
+    if (last_len) last_len[b] = h->path_len;
+    atomicAdd(&sums[0], (unsigned long long)h->sum_path_len);
+    atomicAdd(&sums[1], (unsigned long long)h->n_expanded);
+}
+
+}  // namespace maz

@@ -1,0 +1,61 @@
+// tree_layout.h -- HBM layout of one batch of search trees (shared by host and device code).
+//
+// One SLAB per tree, slabs back to back in one arena.  Inside a slab every node field is its own
+// array over the tree's P = K*(S+2) node slots (structure of arrays), so that the children of a node --
+// which occupy consecutive slots, as in the reference's pool (cnode.cpp:290-293) -- are read by
+// consecutive lanes of the tree's warp with one coalesced request per field.
+//
+// The reference's per-node SubTreeValueSet (utils.h:18-40: per-depth multisets big/small) becomes a
+// per-TREE append-only value log: entry = (node slot, relative depth, in-big flag | value).  Only
+// min(big) and max(small) of one (node, depth) set are ever queried (utils.cpp:34,59), which a warp
+// gets by scanning the log with a shuffle reduction; moving a value between big and small flips one
+// flag bit.  weighted_sum / tot_weight stay per node and are updated with the reference's exact fp32
+// operation order.
+//
+// The reference's CMinMaxStats multiset (utils.h:42-53) holds exactly one entry per visited non-root
+// node (cnode.cpp:431-446): here it is the per-slot array `qdelta`, reduced over the tree's list of
+// expanded slots at the end of each backup; selection reads the cached (min,max).
+#pragma once
+#include <stdint.h>
+
+namespace maz {
+
+constexpr int kMaxSampledTimes = 32;   // children of a node are scored by one warp
+constexpr int kMtN = 624;              // std::mt19937 state words
+constexpr int kMtChunk = 128;          // raw draws staged per fetch (per warp, in shared memory)
+
+struct TreeHdr {              // 64 bytes at the start of every slab
+    int tot_nodes;            // CTree::tot_nodes
+    int log_len;              // entries in the value log
+    int path_len;             // SearchResult::search_len of the last selection
+    int mt_pos;               // position in the mt19937 output block (624 = regenerate first)
+    float mm_min, mm_max;     // CMinMaxStats: min / max of qdelta over visited non-root nodes
+    int mm_cnt;               // 0 => empty set => normalize() is the identity (utils.cpp:97-98)
+    int n_expanded;           // number of expanded nodes (root included) = next hidden_state_index_x
+    int err;                  // first device-side invariant failure of this tree
+    int sum_path_len;         // statistics: sum of path_len over selections
+    int pad[6];
+};
+static_assert(sizeof(TreeHdr) == 64, "TreeHdr must be 64 bytes");
+
+struct TreeLayout {
+    int B, N, A, K, S;
+    int P;        // node slots per tree = K*(S+2)   (cnode.cpp:562)
+    int L;        // value-log capacity = 1 + S*(S+3)/2 + slack (worst case: one chain)
+    float delta_lb, one_minus_rho, lam;
+    unsigned long long slab_bytes;
+    // byte offsets inside a slab (all multiples of 128)
+    unsigned off_mt, off_prior, off_pred_prob, off_beta, off_beta_hat, off_reward, off_pred_value, off_wsum, off_wtot,
+        off_qdelta, off_visit, off_nchild, off_cbase, off_hidx, off_actions, off_expslot, off_path, off_vskey, off_vsval;
+};
+
+// device error codes stored in TreeHdr::err / the handle's global error word
+enum : int {
+    kErrNone = 0,
+    kErrValueSetInvariant = 1,   // utils.cpp:50 "cur_size+1!=size_lim"
+    kErrPoolExhausted = 2,
+    kErrLogOverflow = 3,
+    kErrPathOverflow = 4,
+};
+
+}  // namespace maz
