@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS simulations/second of the batched sampled-MCTS hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 3m] [--mode joint|seq] [--impl ours|reference]
+
+A "step" is ONE whole search of the workload: B roots x S simulations (prepare -> S x [select -> gather
+hidden -> recurrent_inference -> softmax/beta -> expand+backup] -> readout).  Default workload is
+BASELINE.json configs[1]: SMAC 3m-shaped, 3 agents x 9 actions, 1024 roots x 50 sims, K = 10 sampled
+joint actions, synthetic root hidden states and random-init weights of the reference architecture.
+
+`value`   device-resident throughput: inputs already in HBM, outputs left in HBM; CUDA events.
+`e2e`     the same metric through the public API a worker calls (`SampledMCTS.batch_search`) with HOST
+          buffers: numpy root preparation, H2D of the root tensors from pinned memory, the search, D2H of
+          all readouts.
+`roofline`     the dominant tree kernel (expand+backup) against the measured HBM copy peak.
+`cpu_baseline` the reference CPU path (reference C++ tree compiled into oracle/_ref when available, the
+          reference's Python loop restated, the same weights on torch-CPU) on the box's host cores.
+`--impl reference` times that CPU path alone (the reference arm).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mcts_sims_per_sec"
+UNIT = "root-sims/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="3m")
+    ap.add_argument("--mode", default="joint", choices=["joint", "seq"])
+    ap.add_argument("--roots", type=int, default=0, help="override roots per GPU")
+    ap.add_argument("--sims", type=int, default=0, help="override simulations")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from mazero_b200.synthetic import WORKLOADS
+
+    N, A, B, S, K = WORKLOADS[args.workload]
+    if args.roots:
+        B = args.roots
+    if args.sims:
+        S = args.sims
+    return N, A, B, S, K
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                out["sm_max_mhz"] = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_search(args, N, A, B, S, K, sd, hidden, steps, warmup):
+    """The reference's CPU path: reference C++ tree (oracle/_ref) when built, else the C restatement; the
+    reference's Python loop restated (oracle/search_oracle.py); the same weights on torch CPU."""
+    import torch
+    from mazero_b200.synthetic import SearchConfig
+    from oracle import pyoracle
+    from oracle.model_oracle import OracleMAMuZeroNet, inverse_support_transform
+    from oracle.search_oracle import NetworkOutput, reference_batch_search
+
+    pyoracle.build()
+    kind = "reference" if pyoracle.available("reference") else "port"
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = OracleMAMuZeroNet(N, A).load_reference_state_dict(sd).eval()
+    cfg = SearchConfig(A, S, K)
+    hidden = hidden.float().cpu()
+    with torch.no_grad():
+        pol, vlog = model.prediction(hidden)
+        value = inverse_support_transform(vlog, -5, 5)
+    out0 = NetworkOutput(hidden, np.zeros((B, 1), np.float32), value.numpy(), pol.numpy())
+    cur = None if args.mode == "joint" else 0
+    rs = np.random.RandomState(1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        reference_batch_search(cfg, rs, model, out0, cur, None, N, None, "cpu", add_noise=True, tree_kind=kind)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), kind, cores
+
+
+def run_reference_arm(args):
+    import torch
+    from mazero_b200.synthetic import random_state_dict, root_hidden
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, A, B, S, K = workload(args)
+    # bounded sample of the workload: at most 1024 roots per step (the full 3m configuration)
+    Bs = min(B, 1024)
+    sd = random_state_dict(N, A, seed=0)
+    hidden = root_hidden(Bs, N, seed=0)
+    sec, kind, cores = cpu_reference_search(args, N, A, Bs, S, K, sd, hidden, args.steps, args.warmup)
+    val = Bs * S / sec
+    sample = f"{Bs} roots x {S} sims per step, {args.steps} steps, torch CPU {cores} threads, tree single-threaded"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}-shaped {N} agents x {A} actions, {Bs} roots x {S} sims, K={K}, {args.mode} mode",
+                   "roots": Bs, "sims": S, "sampled_times": K, "mode": args.mode},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from mazero_b200 import build
+    build.build()
+    from mazero_b200.inference import SmacInference
+    from mazero_b200.mcts_sampled import SampledMCTS
+    from mazero_b200.synthetic import NetworkOutput, SearchConfig, random_state_dict, root_hidden
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- mazero_b200 has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, A, B, S, K = workload(args)
+    cur = None if args.mode == "joint" else 0
+    Nt = N if cur is None else 1
+    cfg = SearchConfig(A, S, K)
+    sd = random_state_dict(N, A, seed=0)
+    inf = SmacInference(sd, N, A, device=dev)
+    hidden_host = root_hidden(B, N, seed=rank, pinned=True)
+    hidden_dev = hidden_host.to(dev)
+    pol, vlog = inf.prediction(hidden_dev)
+    value = inf._inv_transform(vlog, inf.vsup)
+    out_host = NetworkOutput(hidden_host, np.zeros((B, 1), np.float32), value.cpu().numpy().reshape(B, 1), pol.cpu().numpy())
+    out_dev = out_host._replace(hidden_state=hidden_dev)
+
+    mcts = SampledMCTS(cfg, np.random.RandomState(1), use_cuda_graph=not args.no_graph)
+    root_off = rank * B
+
+    def api_step(net_out):
+        return mcts.batch_search(inf, net_out, cur, None, N, None, dev, add_noise=True, root_index_offset=root_off)
+
+    first = api_step(out_dev)                       # builds the plan + captures the CUDA graph
+    plan = next(iter(mcts._plans.values()))
+    assert int(first.marginal_visit_count[0, 0].sum()) == S
+
+    # ---- device-resident step: reset + prepare + S simulations (graph) + readout kernel, nothing leaves HBM
+    stream = torch.cuda.current_stream(dev)
+    gather = None
+    if world > 1:   # one exchange per search: root values + visit counts to every rank (learner = rank 0)
+        gather = [torch.empty_like(plan.out_flat) for _ in range(world)]
+
+    def dev_step(seed):
+        plan.tree.reset(seed, cfg.tree_value_stat_delta_lb, cfg.mcts_rho, cfg.mcts_lambda, root_off)
+        plan.tree.prepare(plan.root_r, plan.root_v, plan.root_p, plan.root_b, K, cfg.root_exploration_fraction, plan.root_n)
+        if plan.graph is not None:
+            plan.graph.replay()
+        else:
+            plan._loop()
+        plan.tree.readout_device(cfg.discount, plan.out)
+        if gather is not None:
+            dist.all_gather(gather, plan.out_flat)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def timed(fn, n, w):
+        for i in range(w):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        evs = []
+        for i in range(n):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn(w + i)
+            b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev = timed(lambda i: dev_step(100 + i), args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if sampler else None
+    plan.tree.check()
+
+    # ---- end to end through the public API with host buffers (pinned hidden state, numpy everything else)
+    def e2e_step(i):
+        api_step(out_host)
+
+    # batch_search synchronises internally (it returns numpy); wall-clock == device time here, but keep events
+    ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
+    h2d = hidden_host.numel() * 4 + 4 * (2 * B + 3 * B * Nt * A) + (4 * B * N if cur is not None else 0)
+    d2h = plan.out_flat.numel() * 4
+
+    # ---- per-kernel timing of the tree kernels (eager loop, CUDA events around each launch) ---------------
+    tot_nodes, last_len, sum_len, sum_exp = plan.tree.stats()
+    dbar = sum_len / float(B * S)
+    cbar = float((tot_nodes.sum() - B)) / float(sum_exp)
+    plan.tree.reset(7, cfg.tree_value_stat_delta_lb, cfg.mcts_rho, cfg.mcts_lambda, root_off)
+    plan.tree.prepare(plan.root_r, plan.root_v, plan.root_p, plan.root_b, K, cfg.root_exploration_fraction, plan.root_n)
+    sel_ev, exp_ev = [], []
+    for s in range(S):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(stream)
+        plan.tree.batch_selection_device(cfg.pb_c_base, cfg.pb_c_init, cfg.discount, plan.idx_x, plan.idx_y, plan.act)
+        e[1].record(stream)
+        flat = plan.idx_x.long() * B + plan.rows
+        h = plan.pool.view(-1, N * inf.H).index_select(0, flat)
+        joint = plan.act if cur is None else torch.cat(
+            [plan.factor[:, :cur], plan.act, plan.greedy.view(-1, N).index_select(0, flat)[:, cur + 1:]], dim=1)
+        _, rew, val, logits = inf.recurrent(h, joint, out_hidden=plan.pool[s + 1])
+        if cur is not None:
+            logits = logits[:, cur:cur + 1]
+        p = torch.softmax(logits, dim=-1)
+        bta = (p / p.sum(dim=-1, keepdim=True)).contiguous()
+        p = p.contiguous()
+        e[2].record(stream)
+        plan.tree.batch_expansion_and_backup(s + 1, cfg.discount, K, rew, val, p, bta)
+        e[3].record(stream)
+        sel_ev.append((e[0], e[1]))
+        exp_ev.append((e[2], e[3]))
+    torch.cuda.synchronize(dev)
+    ms_sel = float(np.mean([a.elapsed_time(b) for a, b in sel_ev]))
+    ms_exp = float(np.mean([a.elapsed_time(b) for a, b in exp_ev]))
+    # algorithmic bytes per root-simulation of the expand+backup kernel:
+    #   8 + 8*N*A   reward, value, probs, beta in      16 + C*(4N + 36)  leaf header + per-child fields
+    #   40*(d+1)    backup: visit, wsum/wtot r/w, value-log append, min-max entry r/w
+    bytes_exp = B * (8 + 8 * Nt * A + 16 + cbar * (4 * Nt + 36) + 40 * (dbar + 1))
+    bytes_sel = B * (dbar * (16 + 20 * cbar) + 4 * (2 + Nt))
+    peak, peak_src = peaks()
+    achieved = bytes_exp / (ms_exp * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"k_expand_backup:{args.workload}:{args.mode}")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_sims = world * B * S
+    line = {
+        "metric": METRIC, "value": total_sims / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}-shaped {N} agents x {A} actions, {B} roots/GPU x {S} sims, K={K}, {args.mode} mode",
+                   "roots_per_gpu": B, "sims": S, "sampled_times": K, "mode": args.mode, "tree_agents": Nt,
+                   "inference": inf.mode, "cuda_graph": plan.graph is not None, "l2": "flushed (256 MiB memset) between timed steps",
+                   "mean_search_depth": dbar, "mean_children": cbar, "parallelism": f"roots sharded x{world}"},
+        "e2e": {"value": total_sims / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e, "api": "SampledMCTS.batch_search (host numpy + pinned hidden state)"},
+        "gpu_launches": int(args.steps * (3 + 2 * S)),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_expand_backup", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_exp, "launch_ms": ms_exp,
+                     "k_select": {"algorithmic_bytes_per_launch": bytes_sel, "launch_ms": ms_sel,
+                                  "achieved": bytes_sel / (ms_sel * 1e-3) / 1e9}},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        # bounded sample of the same workload on the host cores (one warm-up + two timed searches)
+        Bs = min(B, 1024)
+        sec, kind, cores = cpu_reference_search(args, N, A, Bs, S, K, sd, root_hidden(Bs, N, seed=0), 2, 1)
+        line["cpu_baseline"] = {"value": Bs * S / sec, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{Bs} roots x {S} sims, 2 timed searches after 1 warm-up; reference C++ tree "
+                                          f"({kind}) single-threaded + torch CPU {cores} threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

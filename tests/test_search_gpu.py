@@ -1,0 +1,128 @@
+"""GPU: the search driver `SampledMCTS.batch_search` (drop-in for mcts_sampled.py:34-200).
+
+* step path  (any model, CUDA tree): reproduces the real reference's known answers exactly;
+* device path (SMAC network, whole loop on the GPU, CUDA graph): every simulation's network outputs are
+  recorded and REPLAYED through the CPU oracle tree -- selections, sampled sets and visit counts must be
+  bit-exact, values/Q bit-exact too (same injected fp32 arrays);  graph replay == eager loop."""
+import numpy as np
+import pytest
+import torch
+
+from _mock import MockConfig, MockModel, sequential_search
+from test_search_oracle import check_kat, kat_legal
+
+pytestmark = pytest.mark.gpu
+
+
+def smac_model(n, a, h=128, seed=0):
+    from oracle.model_oracle import OracleMAMuZeroNet
+
+    m = OracleMAMuZeroNet(n, a, hidden_state_size=h, fc_dynamic_layers=(h, h)).init_like_reference(seed).eval()
+    # the reference init leaves the heads at ~0 (uniform policy, value 0): perturb for a non-degenerate search
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.03)
+    return m
+
+
+def root_output(model, B, seed=0):
+    from oracle.search_oracle import NetworkOutput
+
+    g = torch.Generator().manual_seed(seed)
+    hidden = torch.randn(B, model.num_agents * model.hidden, generator=g)
+    with torch.no_grad():
+        pol, vlog = model.prediction(hidden)
+        from oracle.model_oracle import inverse_support_transform
+        value = inverse_support_transform(vlog, -5, 5)
+    return NetworkOutput(hidden, np.zeros((B, 1), np.float32), value.numpy(), pol.numpy())
+
+
+def test_step_path_reproduces_reference_known_answers(built_lib):
+    from mazero_b200.mcts_sampled import SampledMCTS
+
+    cfg, model = MockConfig(), MockModel(2, 3)
+    mcts = SampledMCTS(cfg, np.random.RandomState(123))
+    fn = lambda m, o, k, f, n, l: mcts.batch_search(m, o, k, f, n, l, torch.device("cpu"), add_noise=True)
+    check_kat(*sequential_search(fn, cfg, model, legal=kat_legal()))
+
+
+@pytest.mark.parametrize("cur", [None, 0, 1, 2])
+def test_device_path_replays_bit_exact_through_oracle_tree(built_lib, oracle_built, cur):
+    from mazero_b200.inference import SmacInference
+    from mazero_b200.mcts_sampled import SampledMCTS
+
+    N, A, B, K, S = 3, 9, 48, 10, 25
+    cfg = MockConfig(N, A, S, K)
+    model = smac_model(N, A)
+    inf = SmacInference.from_model(model, device="cuda:0")
+    out0 = root_output(model, B)
+    out0 = out0._replace(hidden_state=out0.hidden_state.cuda())
+    factor = np.random.RandomState(5).randint(0, A, size=(B, N)).astype(np.int32)
+    legal = (np.random.RandomState(6).rand(B, N, A) < 0.7).astype(np.float32)
+    legal[..., 1] = 1
+
+    def run(graph, record):
+        mcts = SampledMCTS(cfg, np.random.RandomState(1), use_cuda_graph=graph)
+        if record is not None:
+            mcts.batch_search(inf, out0, cur, factor, N, legal, "cuda:0", add_noise=True)  # builds the plan
+            plan = next(iter(mcts._plans.values()))
+            plan.record = record
+            mcts.np_random = np.random.RandomState(1)
+        return mcts.batch_search(inf, out0, cur, factor, N, legal, "cuda:0", add_noise=True), mcts
+
+    rec = []
+    eager, mcts = run(False, rec)
+    assert len(rec) == S
+    # replay the recorded network outputs through the CPU oracle tree with the same seed / root arrays
+    plan = next(iter(mcts._plans.values()))
+    Nt = N if cur is None else 1
+    seed = np.random.RandomState(1)
+    seed.dirichlet([cfg.root_dirichlet_alpha] * A, B * Nt if cur is None else B)
+    tree_seed = seed.choice(256)
+    orc = oracle_built.OracleTreeBatch(B, Nt, A, K, S, cfg.tree_value_stat_delta_lb, tree_seed, cfg.mcts_rho, cfg.mcts_lambda)
+    orc.prepare(plan.root_r.cpu().numpy(), plan.root_v.cpu().numpy(), plan.root_p.cpu().numpy(), plan.root_b.cpu().numpy(),
+                K, cfg.root_exploration_fraction, plan.root_n.cpu().numpy())
+    for s, (rew, val, p, b, ix, act) in enumerate(rec):
+        oix, _, oact = orc.batch_selection(cfg.pb_c_base, cfg.pb_c_init, cfg.discount)
+        assert np.array_equal(np.asarray(oix, np.int32), ix.cpu().numpy()), f"sim {s}: hidden_state_index_x"
+        assert np.array_equal(oact, act.cpu().numpy()), f"sim {s}: selected actions"
+        orc.batch_expansion_and_backup(s + 1, cfg.discount, K, rew.cpu().numpy(), val.cpu().numpy(), p.cpu().numpy(), b.cpu().numpy())
+    ro = orc.readout(cfg.discount)
+    assert np.array_equal(eager.marginal_visit_count, orc.get_roots_marginal_visit_count())
+    assert np.array_equal(eager.value, orc.get_roots_values())
+    for b in range(B):
+        n = ro["num_children"][b]
+        assert np.array_equal(eager.sampled_actions[b], ro["actions"][b, :n])
+        assert np.array_equal(eager.sampled_visit_count[b], ro["visit_count"][b, :n])
+        assert np.array_equal(eager.sampled_qvalues[b], ro["qvalues"][b, :n])
+    assert int(eager.marginal_visit_count[0, 0].sum()) == S
+
+    graphed, _ = run(True, None)
+    graphed2 = None
+    for f in eager._fields:
+        x, y = getattr(eager, f), getattr(graphed, f)
+        if isinstance(x, np.ndarray):
+            assert np.array_equal(x, y), f
+        else:
+            assert x == y, f
+
+
+def test_device_path_accepts_reference_style_module(built_lib):
+    """A torch module with the reference's parameter names on the GPU is adapted automatically."""
+    from mazero_b200.mcts_sampled import SampledMCTS
+
+    N, A, B, K, S = 3, 9, 16, 5, 10
+    cfg = MockConfig(N, A, S, K)
+    model = smac_model(N, A).cuda()
+    model.hidden_state_size_per_agent = model.hidden
+    out0 = root_output(smac_model(N, A), B)
+    out0 = out0._replace(hidden_state=out0.hidden_state.cuda())
+    mcts = SampledMCTS(cfg, np.random.RandomState(3))
+    o = mcts.batch_search(model, out0, 0, None, N, None, torch.device("cuda:0"), add_noise=False)
+    assert len(mcts._plans) == 1
+    assert o.value.shape == (B,) and o.marginal_visit_count.shape == (B, 1, A)
+    assert (o.marginal_visit_count.sum(axis=(1, 2)) == S).all()
+    assert all(o.sampled_actions[b].shape[1] == 1 for b in range(B))
+    with pytest.raises(NotImplementedError):
+        mcts.batch_search(model, out0, 0, None, N, None, torch.device("cuda:0"), sampled_actions_res=(None, None))
