@@ -33,18 +33,34 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+# per-file flags: the tree engine must not contract a*b+c (bit-exact with x86-64 reference code);
+# the inference kernels are ordinary floating point and want FMAs.
+FILE_FLAGS = {"maz_tree.cu": ["-fmad=false"]}
+
+
 def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT
-    cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC,-O2",
-           "-shared", "-o", OUT, *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs, log = [], ""
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", *FILE_FLAGS.get(os.path.basename(src), []),
+               "-Xcompiler", "-fPIC,-O2", "-c", "-o", obj, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        log += res.stdout + res.stderr
+        objs.append(obj)
+    cmd = [_nvcc(), *ARCH, "-shared", "-o", OUT, *objs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stdout + res.stderr)
+        print(log)
     return OUT
 
 

@@ -1,0 +1,90 @@
+// maz_infer.cu -- fused network forward for the search (tcgen05 / TMEM / bulk-TMA, sm_100a).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/maz_infer.h"
+#include "umma.cuh"
+
+using namespace maz;
+using namespace maz::umma;
+
+extern "C" const char *maz_last_error(void);
+namespace maz { int set_last_error(int code, const std::string &msg); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Self-test kernel: one GEMM stage exactly as the fused kernel runs it.
+//   threads: 128 (4 warps); thread r owns token row r.
+__global__ void __launch_bounds__(128, 1) k_dbg_umma_gemm(const float *__restrict__ a, const __nv_bfloat16 *__restrict__ wp,
+                                                          float *__restrict__ out, int N, int K)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_w, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *sA = smem;                                   // 128 x K bf16
+    uint8_t *sW = smem + operand_bytes(128, K);           // N x K bf16
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(&bar_w, 1);
+        mbar_init(&bar_mma, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (tid == 0) {
+        mbar_expect_tx(&bar_w, operand_bytes(N, K));
+        bulk_g2s(sW, wp, operand_bytes(N, K), &bar_w);
+    }
+    // activations: fp32 global row -> bf16 operand layout
+    for (int k8 = 0; k8 < K / 8; ++k8) {
+        const float4 lo = *reinterpret_cast<const float4 *>(a + (size_t)tid * K + k8 * 8);
+        const float4 hi = *reinterpret_cast<const float4 *>(a + (size_t)tid * K + k8 * 8 + 4);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
+        uint4 v;
+        v.x = *reinterpret_cast<uint32_t *>(&p0);
+        v.y = *reinterpret_cast<uint32_t *>(&p1);
+        v.z = *reinterpret_cast<uint32_t *>(&p2);
+        v.w = *reinterpret_cast<uint32_t *>(&p3);
+        *reinterpret_cast<uint4 *>(sA + chunk_off(tid, k8, K)) = v;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        mbar_wait(&bar_w, 0);
+        tc_fence_after();
+        issue_gemm(tmem_base, smem_u32(sA), K, 0, smem_u32(sW), K, 0, K, N, false);
+        mma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld16(lane_base + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out[(size_t)tid * N + c + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+extern "C" int maz_dbg_umma_gemm(const float *a, const void *w_packed, float *out, int n, int k, void *stream)
+{
+    if (!a || !w_packed || !out || n % 16 || k % 16 || n < 16 || n > 256 || k < 16 || k > 512)
+        return set_last_error(1, "maz_dbg_umma_gemm: bad arguments");
+    const size_t dyn = operand_bytes(128, k) + operand_bytes(n, k) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(k_dbg_umma_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return set_last_error(2, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    k_dbg_umma_gemm<<<1, 128, dyn, static_cast<cudaStream_t>(stream)>>>(a, static_cast<const __nv_bfloat16 *>(w_packed), out, n, k);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_last_error(2, std::string("k_dbg_umma_gemm: ") + cudaGetErrorString(e));
+    return 0;
+}

@@ -20,6 +20,9 @@ static int set_err(int code, const std::string &msg)
     g_last_error = msg;
     return code;
 }
+namespace maz {
+int set_last_error(int code, const std::string &msg) { return set_err(code, msg); }  // shared with maz_infer.cu
+}
 
 #define CU_TRY(expr)                                                                                          \
     do {                                                                                                      \
