@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--sims", type=int, default=0, help="override simulations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--inference", default="bf16", choices=["bf16", "fp32"], help="bf16 = fused tcgen05 kernel, fp32 = parity mode")
     return ap.parse_args()
 
 
@@ -66,6 +67,15 @@ def peaks():
         j = json.load(open(p))
         return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# algorithmic FLOPs of one recurrent_inference per root (SURVEY.md 8d / BASELINE.md section 4)
+FLOP_PER_ROOT = {"3m": 2.61e6, "2s3z": 4.36e6, "mmm2": 8.81e6, "27m": 24.41e6}
+
+
+def bf16_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["bf16_tflops_sustained"]) if os.path.exists(p) else 1400.0
 
 
 class ClockSampler:
@@ -196,7 +206,7 @@ def run_ours(args):
     Nt = N if cur is None else 1
     cfg = SearchConfig(A, S, K)
     sd = random_state_dict(N, A, seed=0)
-    inf = SmacInference(sd, N, A, device=dev)
+    inf = SmacInference(sd, N, A, device=dev, mode=args.inference)
     hidden_host = root_hidden(B, N, seed=rank, pinned=True)
     hidden_dev = hidden_host.to(dev)
     pol, vlog = inf.prediction(hidden_dev)
@@ -279,7 +289,7 @@ def run_ours(args):
     cbar = float((tot_nodes.sum() - B)) / float(sum_exp)
     plan.tree.reset(7, cfg.tree_value_stat_delta_lb, cfg.mcts_rho, cfg.mcts_lambda, root_off)
     plan.tree.prepare(plan.root_r, plan.root_v, plan.root_p, plan.root_b, K, cfg.root_exploration_fraction, plan.root_n)
-    sel_ev, exp_ev = [], []
+    sel_ev, exp_ev, inf_ev = [], [], []
     # keep the GPU busy while the host enqueues the whole eager loop, so that the event pairs bracket
     # back-to-back GPU execution and not host launch latency
     torch.cuda._sleep(int(2.0e8))
@@ -289,15 +299,24 @@ def run_ours(args):
         plan.tree.batch_selection_device(cfg.pb_c_base, cfg.pb_c_init, cfg.discount, plan.idx_x, plan.idx_y, plan.act)
         e[1].record(stream)
         flat = plan.idx_x.long() * B + plan.rows
-        h = plan.pool.view(-1, N * inf.H).index_select(0, flat)
         joint = plan.act if cur is None else torch.cat(
-            [plan.factor[:, :cur], plan.act, plan.greedy.view(-1, N).index_select(0, flat)[:, cur + 1:]], dim=1)
-        _, rew, val, logits = inf.recurrent(h, joint, out_hidden=plan.pool[s + 1])
-        if cur is not None:
-            logits = logits[:, cur:cur + 1]
-        p = torch.softmax(logits, dim=-1)
-        bta = (p / p.sum(dim=-1, keepdim=True)).contiguous()
-        p = p.contiguous()
+            [plan.factor[:, :cur], plan.act, plan.greedy.view(-1, N).index_select(0, flat)[:, cur + 1:]], dim=1).contiguous()
+        if inf.fused is not None:
+            ei = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ei[0].record(stream)
+            inf.recurrent_fused(B, plan.pool, plan.idx_x, joint, plan.pool[s + 1], plan.sim_r, plan.sim_v, plan.sim_p, plan.sim_b,
+                                plan.greedy[s + 1] if cur is not None else None, None, Nt, -1 if cur is None else cur, 1.0)
+            ei[1].record(stream)
+            inf_ev.append(ei)
+            rew, val, p, bta = plan.sim_r, plan.sim_v, plan.sim_p, plan.sim_b
+        else:
+            h = plan.pool.view(-1, N * inf.H).index_select(0, flat)
+            _, rew, val, logits = inf.recurrent(h, joint, out_hidden=plan.pool[s + 1])
+            if cur is not None:
+                logits = logits[:, cur:cur + 1]
+            p = torch.softmax(logits, dim=-1)
+            bta = (p / p.sum(dim=-1, keepdim=True)).contiguous()
+            p = p.contiguous()
         e[2].record(stream)
         plan.tree.batch_expansion_and_backup(s + 1, cfg.discount, K, rew, val, p, bta)
         e[3].record(stream)
@@ -306,6 +325,7 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     ms_sel = float(np.mean([a.elapsed_time(b) for a, b in sel_ev]))
     ms_exp = float(np.mean([a.elapsed_time(b) for a, b in exp_ev]))
+    ms_inf = float(np.mean([a.elapsed_time(b) for a, b in inf_ev])) if inf_ev else None
     # algorithmic bytes per root-simulation of the expand+backup kernel:
     #   8 + 8*N*A   reward, value, probs, beta in      16 + C*(4N + 36)  leaf header + per-child fields
     #   40*(d+1)    backup: visit, wsum/wtot r/w, value-log append, min-max entry r/w
@@ -327,20 +347,24 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": total_sims / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "bf16" if inf.fused is not None else "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}-shaped {N} agents x {A} actions, {B} roots/GPU x {S} sims, K={K}, {args.mode} mode",
                    "roots_per_gpu": B, "sims": S, "sampled_times": K, "mode": args.mode, "tree_agents": Nt,
                    "inference": inf.mode, "cuda_graph": plan.graph is not None, "l2": "flushed (256 MiB memset) between timed steps",
                    "mean_search_depth": dbar, "mean_children": cbar, "parallelism": f"roots sharded x{world}"},
         "e2e": {"value": total_sims / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e, "api": "SampledMCTS.batch_search (host numpy + pinned hidden state)"},
-        "gpu_launches": int(args.steps * (3 + 2 * S)),
+        "gpu_launches": int(args.steps * (3 + (3 if inf.fused is not None else 2) * S)),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_expand_backup", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_exp, "launch_ms": ms_exp,
                      "k_select": {"algorithmic_bytes_per_launch": bytes_sel, "launch_ms": ms_sel,
-                                  "achieved": bytes_sel / (ms_sel * 1e-3) / 1e9}},
+                                  "achieved": bytes_sel / (ms_sel * 1e-3) / 1e9},
+                     "k_recurrent_inference": None if ms_inf is None else {
+                         "bound": "tensor", "launch_ms": ms_inf, "flop_per_launch": B * FLOP_PER_ROOT.get(args.workload, 0.0),
+                         "achieved_tflops": B * FLOP_PER_ROOT.get(args.workload, 0.0) / (ms_inf * 1e-3) / 1e12,
+                         "peak_tflops": bf16_peak()}},
     }
     if not args.no_cpu_baseline and world == 1:
         # bounded sample of the same workload on the host cores (one warm-up + two timed searches)

@@ -20,6 +20,33 @@ extern "C" {
  * W.view(n/8, 8, k/8, 8).permute(0, 2, 1, 3).  n, k multiples of 16, n <= 256, k <= 512. */
 int maz_dbg_umma_gemm(const float *a, const void *w_packed, float *out, int n, int k, void *cuda_stream);
 
+/* Everything one launch of the fused recurrent_inference kernel needs.  All pointers are DEVICE pointers.
+ * Fixed architecture (config/smac/__init__.py:15-27): hidden 128 per agent, 3 encoder layers x 8 heads,
+ * dim_feedforward 128, fc_dynamic [128,128], GNN hidden 64, fc_policy [32], support 11; agents N <= 32,
+ * actions A <= 48.  Weight packing: see mazero_b200/fused.py (pack_weights). */
+#define MAZ_INFER_NCHUNK 30
+typedef struct maz_infer_desc {
+    int B, N, A, KA, NAP;        /* roots, agents, actions, A rounded up to 16 (twice) */
+    int Nt, cur;                 /* agents in the tree (N joint / 1 sequential), sequential agent index or -1 */
+    float inv_tau;               /* 1 / sampled_tau (mcts_sampled.py:160) */
+    const float *pool;           /* hidden-state pool: row (idx*B + b), N*128 floats */
+    const int *idx_x;            /* (B,) pool index of the parent of each root's leaf, or NULL (= 0) */
+    const int *actions;          /* (B,N) joint action */
+    float *next_hidden;          /* (B, N*128) */
+    float *reward, *value;       /* (B,) scalars after the inverse support transform */
+    float *probs, *beta;         /* (B,Nt,A) softmax of the policy logits and probs^(1/tau) renormalised */
+    int *greedy;                 /* (B,N) argmax_a of the policy logits, or NULL */
+    float *logits_out;           /* (B,N,A) raw policy logits, or NULL */
+    const void *wpk;             /* bf16 weight chunks in tcgen05 operand layout */
+    const float *vec;            /* fp32 biases / LayerNorm affine / positional table / heads */
+    unsigned int chunk_off[MAZ_INFER_NCHUNK];
+    unsigned int chunk_bytes[MAZ_INFER_NCHUNK];
+    int o_bin, o_pos, o_layer, o_dyn, o_rg, o_vg, o_pol;   /* float offsets into vec */
+} maz_infer_desc;
+
+/* replaces model.recurrent_inference + the driver's softmax/beta (mcts_sampled.py:150-161): one kernel launch */
+int maz_infer_recurrent(const maz_infer_desc *desc, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,7 @@ SIGNATURES = {
     "maz_tree_arena_bytes": (C.c_size_t, [C.c_void_p]),
     # include/maz_infer.h
     "maz_dbg_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "maz_infer_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 if not os.path.exists(LIB_PATH):

@@ -6,6 +6,7 @@
 
 #include "../../include/maz_infer.h"
 #include "umma.cuh"
+#include "infer_fused.cuh"
 
 using namespace maz;
 using namespace maz::umma;
@@ -86,5 +87,27 @@ extern "C" int maz_dbg_umma_gemm(const float *a, const void *w_packed, float *ou
     k_dbg_umma_gemm<<<1, 128, dyn, static_cast<cudaStream_t>(stream)>>>(a, static_cast<const __nv_bfloat16 *>(w_packed), out, n, k);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_last_error(2, std::string("k_dbg_umma_gemm: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
+{
+    if (!d) return set_last_error(1, "maz_infer_recurrent: NULL descriptor");
+    if (d->B <= 0 || d->N <= 0 || d->N > 32 || d->A <= 0 || d->A > 48 || d->KA % 16 || d->KA < d->A || d->NAP != d->KA)
+        return set_last_error(3, "maz_infer_recurrent: unsupported shape (agents <= 32, actions <= 48)");
+    if (!d->pool || !d->actions || !d->next_hidden || !d->reward || !d->value || !d->probs || !d->beta || !d->wpk || !d->vec)
+        return set_last_error(1, "maz_infer_recurrent: NULL tensor");
+    const size_t dyn = fused::smem_bytes(d->KA);
+    static size_t configured = 0;
+    if (dyn > configured) {
+        cudaError_t e = cudaFuncSetAttribute(fused::k_recurrent_inference, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return set_last_error(2, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+        configured = dyn;
+    }
+    const int roots_per_tile = 4 * (32 / d->N);
+    const int tiles = (d->B + roots_per_tile - 1) / roots_per_tile;
+    fused::k_recurrent_inference<<<tiles, 128, dyn, static_cast<cudaStream_t>(stream)>>>(*d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_last_error(2, std::string("k_recurrent_inference: ") + cudaGetErrorString(e));
     return 0;
 }

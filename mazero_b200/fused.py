@@ -1,0 +1,165 @@
+"""Host side of the fused tensor-core inference kernel (include/maz_infer.h, csrc/infer_fused.cuh):
+packs a reference-named state dict into (a) bf16 weight chunks in the tcgen05 shared-memory operand layout,
+in the order the kernel consumes them, and (b) one fp32 vector of biases / LayerNorm affines / positional
+table / value & reward heads; fills the launch descriptor.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib
+
+NCHUNK = 30
+H, GH, PH, SUP = 128, 64, 32, 11
+
+
+class InferDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("N", C.c_int), ("A", C.c_int), ("KA", C.c_int), ("NAP", C.c_int), ("Nt", C.c_int), ("cur", C.c_int),
+        ("inv_tau", C.c_float),
+        ("pool", C.c_void_p), ("idx_x", C.c_void_p), ("actions", C.c_void_p), ("next_hidden", C.c_void_p),
+        ("reward", C.c_void_p), ("value", C.c_void_p), ("probs", C.c_void_p), ("beta", C.c_void_p), ("greedy", C.c_void_p),
+        ("logits_out", C.c_void_p), ("wpk", C.c_void_p), ("vec", C.c_void_p),
+        ("chunk_off", C.c_uint * NCHUNK), ("chunk_bytes", C.c_uint * NCHUNK),
+        ("o_bin", C.c_int), ("o_pos", C.c_int), ("o_layer", C.c_int), ("o_dyn", C.c_int), ("o_rg", C.c_int),
+        ("o_vg", C.c_int), ("o_pol", C.c_int),
+    ]
+
+
+def _pad16(n):
+    return (n + 15) // 16 * 16
+
+
+def pack_operand(w):
+    """[rows, K] fp32 -> bf16, K-major core-matrix layout: W.view(rows/8, 8, K/8, 8).permute(0, 2, 1, 3)."""
+    r, k = w.shape
+    assert r % 8 == 0 and k % 16 == 0, (r, k)
+    return w.to(torch.bfloat16).view(r // 8, 8, k // 8, 8).permute(0, 2, 1, 3).contiguous().view(-1)
+
+
+def _padcols(w, k):
+    out = torch.zeros(w.shape[0], k, dtype=w.dtype, device=w.device)
+    out[:, : w.shape[1]] = w
+    return out
+
+
+def _padrows(w, r):
+    out = torch.zeros(r, w.shape[1], dtype=w.dtype, device=w.device)
+    out[: w.shape[0]] = w
+    return out
+
+
+def supported(sd, num_agents, action_space_size, hidden):
+    d = "dynamics_network."
+    try:
+        return (hidden == H and num_agents <= 32 and action_space_size <= 48
+                and f"{d}attention_stack.2.encoder.layers.2.linear1.weight" in sd
+                and f"{d}attention_stack.2.encoder.layers.3.linear1.weight" not in sd
+                and sd[f"{d}attention_stack.2.encoder.layers.0.linear1.weight"].shape == (H, H)
+                and sd[f"{d}fc_dynamic.3.weight"].shape == (H, H) and f"{d}fc_dynamic.6.weight" in sd
+                and f"{d}fc_dynamic.9.weight" not in sd
+                and sd[f"{d}reward_predictor.gc1.lin_layer.weight"].shape[0] == GH
+                and sd[f"{d}reward_predictor.V.weight"].shape[0] == SUP
+                and sd["prediction_network.value_predictor.V.weight"].shape[0] == SUP
+                and sd["prediction_network.fc_policy.0.weight"].shape[0] == PH
+                and "prediction_network.fc_policy.3.weight" in sd and "prediction_network.fc_policy.6.weight" not in sd)
+    except KeyError:
+        return False
+
+
+class FusedParams:
+    """Device-resident packed parameters + the constant half of the launch descriptor."""
+
+    def __init__(self, sd, num_agents, action_space_size, device):
+        self.N, self.A = int(num_agents), int(action_space_size)
+        self.KA = _pad16(self.A)
+        self.device = torch.device(device)
+        self.wpk = None
+        self.vec = None
+        self.repack(sd)
+
+    def repack(self, sd):
+        dev, N, A, KA = self.device, self.N, self.A, self.KA
+        g = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32)
+        d, p = "dynamics_network.", "prediction_network."
+        chunks = []
+        w_in = g(d + "attention_stack.0.weight")                       # (128, 128 + A)
+        chunks.append(_padcols(w_in, H + KA))
+        for l in range(3):
+            e = f"{d}attention_stack.2.encoder.layers.{l}."
+            qkv = g(e + "self_attn.in_proj_weight")
+            chunks += [qkv[0:H], qkv[H:2 * H], qkv[2 * H:3 * H], g(e + "self_attn.out_proj.weight"),
+                       g(e + "linear1.weight"), g(e + "linear2.weight")]
+        wd1 = g(d + "fc_dynamic.0.weight")                             # (128, 128 + A + 128)
+        chunks += [wd1[:, :H], _padcols(wd1[:, H:H + A], KA), wd1[:, H + A:], g(d + "fc_dynamic.3.weight"),
+                   g(d + "fc_dynamic.6.weight")]
+        r = d + "reward_predictor."
+        chunks.append(_padcols(torch.cat([g(r + "gc1.lin_layer.weight"), g(r + "nn_gc1.weight")], 0), H + KA))
+        chunks.append(torch.cat([g(r + "gc2.lin_layer.weight"), g(r + "nn_gc2.weight")], 0))
+        v = p + "value_predictor."
+        chunks.append(torch.cat([g(v + "gc1.lin_layer.weight"), g(v + "nn_gc1.weight")], 0))
+        chunks.append(torch.cat([g(v + "gc2.lin_layer.weight"), g(v + "nn_gc2.weight")], 0))
+        chunks.append(g(p + "fc_policy.0.weight"))                     # (32, 128)
+        chunks.append(_padrows(g(p + "fc_policy.3.weight"), KA))       # (KA, 32)
+        assert len(chunks) == NCHUNK
+        packed = [pack_operand(c.contiguous()) for c in chunks]
+        offs, o = [], 0
+        for t in packed:
+            offs.append(o)
+            o += t.numel() * 2
+        wpk = torch.cat(packed)
+        self.chunk_off = offs
+        self.chunk_bytes = [t.numel() * 2 for t in packed]
+
+        vec, self.off = [], {}
+
+        def put(name, *ts):
+            self.off[name] = sum(t.numel() for t in vec)
+            for t in ts:
+                vec.append(t.reshape(-1))
+
+        z16 = torch.zeros(16, device=dev)
+        put("bin", g(d + "attention_stack.0.bias"))
+        put("pos", g(d + "attention_stack.2.pos_embed.pos_table")[0, :N].contiguous())
+        self.off["layer"] = sum(t.numel() for t in vec)
+        for l in range(3):
+            e = f"{d}attention_stack.2.encoder.layers.{l}."
+            qb = g(e + "self_attn.in_proj_bias")
+            vec += [qb, g(e + "self_attn.out_proj.bias"), g(e + "norm1.weight"), g(e + "norm1.bias"), g(e + "linear1.bias"),
+                    g(e + "linear2.bias"), g(e + "norm2.weight"), g(e + "norm2.bias")]
+        put("dyn", g(d + "fc_dynamic.0.bias"), g(d + "fc_dynamic.1.weight"), g(d + "fc_dynamic.1.bias"),
+            g(d + "fc_dynamic.3.bias"), g(d + "fc_dynamic.4.weight"), g(d + "fc_dynamic.4.bias"), g(d + "fc_dynamic.6.bias"))
+        for name, pre in (("rg", r), ("vg", v)):
+            put(name, g(pre + "gc1.lin_layer.bias"), g(pre + "nn_gc1.bias"), g(pre + "gc2.lin_layer.bias"), g(pre + "nn_gc2.bias"),
+                g(pre + "V.weight"), torch.cat([g(pre + "V.bias"), z16[: 16 - SUP]]))
+        bp2 = torch.cat([g(p + "fc_policy.3.bias"), torch.zeros(KA - A, device=dev)])
+        put("pol", g(p + "fc_policy.0.bias"), g(p + "fc_policy.1.weight"), g(p + "fc_policy.1.bias"), bp2)
+        vecf = torch.cat(vec).contiguous()
+        assert all(o % 4 == 0 for o in self.off.values())
+        if self.wpk is None:
+            self.wpk, self.vec = wpk, vecf
+        else:                      # keep addresses stable for captured CUDA graphs
+            self.wpk.copy_(wpk)
+            self.vec.copy_(vecf)
+
+    def desc(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None, logits_out=None,
+             tree_agents=None, cur=-1, inv_tau=1.0):
+        ptr = lambda t: (t.data_ptr() if t is not None else None)
+        dsc = InferDesc()
+        dsc.B, dsc.N, dsc.A, dsc.KA, dsc.NAP = int(B), self.N, self.A, self.KA, self.KA
+        dsc.Nt = self.N if tree_agents is None else int(tree_agents)
+        dsc.cur, dsc.inv_tau = int(cur), float(inv_tau)
+        dsc.pool, dsc.idx_x, dsc.actions, dsc.next_hidden = ptr(pool), ptr(idx_x), ptr(actions), ptr(next_hidden)
+        dsc.reward, dsc.value, dsc.probs, dsc.beta = ptr(reward), ptr(value), ptr(probs), ptr(beta)
+        dsc.greedy, dsc.logits_out = ptr(greedy), ptr(logits_out)
+        dsc.wpk, dsc.vec = self.wpk.data_ptr(), self.vec.data_ptr()
+        for i in range(NCHUNK):
+            dsc.chunk_off[i], dsc.chunk_bytes[i] = self.chunk_off[i], self.chunk_bytes[i]
+        o = self.off
+        dsc.o_bin, dsc.o_pos, dsc.o_layer, dsc.o_dyn = o["bin"], o["pos"], o["layer"], o["dyn"]
+        dsc.o_rg, dsc.o_vg, dsc.o_pol = o["rg"], o["vg"], o["pol"]
+        return dsc
+
+
+def launch(dsc, stream_ptr):
+    check(lib.maz_infer_recurrent(C.byref(dsc), C.c_void_p(stream_ptr)))

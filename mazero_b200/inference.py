@@ -91,6 +91,18 @@ class SmacInference:
             idx += 3
         self.rsup = torch.arange(reward_support[0], reward_support[1] + 1, dtype=torch.float32, device=dev)
         self.vsup = torch.arange(value_support[0], value_support[1] + 1, dtype=torch.float32, device=dev)
+        # fused tensor-core path (bf16 operands, fp32 accumulate): csrc/infer_fused.cuh
+        self.fused = None
+        if mode == "bf16":
+            from . import fused
+
+            if dev.type != "cuda":
+                raise RuntimeError("mode='bf16' needs a CUDA device (no CPU fallback)")
+            if tuple(reward_support) != (-5, 5) or tuple(value_support) != (-5, 5) or nhead != 8 or \
+                    not fused.supported(sd, self.N, self.A, self.H):
+                raise RuntimeError("mode='bf16': network shape not supported by the fused kernel "
+                                   "(needs the reference SMAC architecture: hidden 128, 3 layers, 8 heads, support 11)")
+            self.fused = fused.FusedParams(self._params, self.N, self.A, dev)
 
     @classmethod
     def from_model(cls, model, device="cuda", mode="fp32", **kw):
@@ -108,6 +120,18 @@ class SmacInference:
             src = state_dict[k]
             if src.data_ptr() != t.data_ptr():
                 t.copy_(src, non_blocking=True)
+        if self.fused is not None:
+            self.fused.repack(self._params)
+
+    def recurrent_fused(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None,
+                        logits_out=None, tree_agents=None, cur=-1, inv_tau=1.0, stream=None):
+        """One launch of the fused kernel: gather parent hidden from `pool` by `idx_x`, recurrent_inference,
+        inverse support transforms, softmax / beta of the tree agents.  Everything stays on the device."""
+        from . import fused
+
+        dsc = self.fused.desc(B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy, logits_out,
+                              tree_agents, cur, inv_tau)
+        fused.launch(dsc, (stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream)
 
     # ---- pieces ----------------------------------------------------------------------------------------
     @staticmethod

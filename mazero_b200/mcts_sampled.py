@@ -103,6 +103,9 @@ class _DevicePlan:
         z = lambda *s: torch.zeros(*s, dtype=f32, device=dev)
         self.root_r, self.root_v = z(B), z(B)
         self.root_p, self.root_b, self.root_n = z(B, self.Nt, self.A), z(B, self.Nt, self.A), z(B, self.Nt, self.A)
+        # per-simulation network outputs (fused path writes them in place)
+        self.sim_r, self.sim_v = z(B), z(B)
+        self.sim_p, self.sim_b = z(B, self.Nt, self.A), z(B, self.Nt, self.A)
         self.graph = None
         self.use_graph = use_graph
         self.record = None  # when a list: per-simulation injected arrays are appended (parity replay tests)
@@ -126,13 +129,27 @@ class _DevicePlan:
     def _simulate(self, s):
         t, B = self.tree, self.B
         t.batch_selection_device(self.c_base, self.c_init, self.discount, self.idx_x, self.idx_y, self.act)
-        flat = self.idx_x.long() * B + self.rows                              # row of the parent in the pool
-        h = self.pool.view(-1, self.N * self.H).index_select(0, flat)
+        flat = None
         if self.cur is None:
             joint = self.act
         else:                                                                 # mcts_sampled.py:116-147
+            flat = self.idx_x.long() * B + self.rows                          # row of the parent in the pool
             g = self.greedy.view(-1, self.N).index_select(0, flat)
-            joint = torch.cat([self.factor[:, : self.cur], self.act, g[:, self.cur + 1:]], dim=1)
+            joint = torch.cat([self.factor[:, : self.cur], self.act, g[:, self.cur + 1:]], dim=1).contiguous()
+        if self.inf.fused is not None:
+            # ONE kernel: gather parent hidden, recurrent_inference on the tensor cores, inverse support
+            # transforms, softmax / beta of the tree agents, greedy actions of every agent
+            self.inf.recurrent_fused(B, self.pool, self.idx_x, joint, self.pool[s + 1], self.sim_r, self.sim_v, self.sim_p,
+                                     self.sim_b, self.greedy[s + 1] if self.cur is not None else None, None, self.Nt,
+                                     -1 if self.cur is None else self.cur, 1.0 / self.tau)
+            if self.record is not None:
+                self.record.append((self.sim_r.clone(), self.sim_v.clone(), self.sim_p.clone(), self.sim_b.clone(),
+                                    self.idx_x.clone(), self.act.clone()))
+            t.batch_expansion_and_backup(s + 1, self.discount, self.K, self.sim_r, self.sim_v, self.sim_p, self.sim_b)
+            return
+        if flat is None:
+            flat = self.idx_x.long() * B + self.rows
+        h = self.pool.view(-1, self.N * self.H).index_select(0, flat)
         _, rew, val, logits = self.inf.recurrent(h, joint, out_hidden=self.pool[s + 1])
         if self.cur is not None:
             self.greedy[s + 1].copy_(logits.argmax(dim=-1))
@@ -201,10 +218,14 @@ class _DevicePlan:
 
 
 class SampledMCTS(object):
-    def __init__(self, config, np_random: np.random.RandomState = None, use_cuda_graph: bool = True):
+    def __init__(self, config, np_random: np.random.RandomState = None, use_cuda_graph: bool = True,
+                 inference_mode: str = "auto"):
+        """inference_mode: "bf16" = fused tensor-core kernel, "fp32" = parity mode (plain fp32 torch ops on the
+        device), "auto" = bf16 when the network has the reference SMAC architecture, else fp32."""
         self.config = config
         self.np_random = np.random if np_random is None else np_random
         self.use_cuda_graph = use_cuda_graph
+        self.inference_mode = inference_mode
         self._inference = {}
         self._plans = {}
 
@@ -225,11 +246,20 @@ class SampledMCTS(object):
             return None
         key = (id(model), str(dev))
         inf = self._inference.get(key)
+        version = sum(int(getattr(p, "_version", 0)) for p in sd.values())
         if inf is None:
-            inf = SmacInference.from_model(model, device=dev)
+            mode = self.inference_mode
+            if mode == "auto":
+                from . import fused
+
+                h = int(getattr(model, "hidden_state_size_per_agent", getattr(model, "hidden", 128)))
+                mode = "bf16" if fused.supported(sd, int(model.num_agents), int(model.action_space_size), h) else "fp32"
+            inf = SmacInference.from_model(model, device=dev, mode=mode)
+            inf._src_version = version
             self._inference[key] = inf
-        else:
+        elif getattr(inf, "_src_version", None) != version:   # weights were updated in place (set_weights)
             inf.refresh(sd)
+            inf._src_version = version
         return inf
 
     # ---- the entry point (mcts_sampled.py:34-46) -----------------------------------------------------------

@@ -30,3 +30,55 @@ def test_umma_gemm_stage(built_lib, n, k):
     ref = a.to(torch.bfloat16).float() @ w.to(torch.bfloat16).float().t()   # bf16 operands, fp32 accumulate
     err = (out - ref).abs().max().item()
     assert err < 2e-3, f"max abs err {err}"     # fp32 accumulation-order noise only
+
+
+@pytest.mark.parametrize("N,A,B", [(3, 9, 100), (5, 11, 70), (10, 18, 33), (27, 36, 9), (1, 5, 130), (2, 3, 16)])
+def test_fused_recurrent_inference_matches_fp32_reference(built_lib, N, A, B):
+    """bf16 tensor-core kernel vs the plain fp32 torch forward (same weights).  Tolerance: bf16 operand
+    rounding (2^-8 relative) through ~20 chained GEMMs -> 2% of each tensor's dynamic range (max |ref|,
+    at least 1); probabilities 1e-2 absolute."""
+    from mazero_b200.inference import SmacInference
+    from mazero_b200.synthetic import random_state_dict
+
+    dev = torch.device("cuda:0")
+    sd = random_state_dict(N, A, seed=N, head_scale=30.0)   # heads large enough to give non-uniform policies
+    ref = SmacInference(sd, N, A, device=dev, mode="fp32")
+    fus = SmacInference(sd, N, A, device=dev, mode="bf16")
+    g = torch.Generator().manual_seed(B)
+    S = 3
+    pool = torch.randn(S, B, N * 128, generator=g).to(dev)
+    idx = torch.randint(0, S, (B,), generator=g).to(torch.int32).to(dev)
+    act = torch.randint(0, A, (B, N), generator=g).to(torch.int32).to(dev)
+    h = pool.view(-1, N * 128).index_select(0, idx.long() * B + torch.arange(B, device=dev))
+    nxt_ref, rew_ref, val_ref, log_ref = ref.recurrent(h, act)
+
+    nxt = torch.full((B, N * 128), float("nan"), device=dev)
+    rew = torch.full((B,), float("nan"), device=dev)
+    val = torch.full((B,), float("nan"), device=dev)
+    probs = torch.full((B, N, A), float("nan"), device=dev)
+    beta = torch.full((B, N, A), float("nan"), device=dev)
+    logits = torch.full((B, N, A), float("nan"), device=dev)
+    greedy = torch.full((B, N), -1, dtype=torch.int32, device=dev)
+    fus.recurrent_fused(B, pool, idx, act, nxt, rew, val, probs, beta, greedy, logits)
+    torch.cuda.synchronize()
+    for name, x, y, rel in (("next_hidden", nxt, nxt_ref, 2e-2), ("policy_logits", logits, log_ref, 2e-2),
+                            ("reward", rew, rew_ref, 4e-2), ("value", val, val_ref, 4e-2),   # + the steep inv_h transform
+                            ("probs", probs, torch.softmax(log_ref, -1), 1e-2)):
+        assert torch.isfinite(x).all(), name
+        err = (x - y).abs().max().item()
+        tol = rel * max(1.0, y.abs().max().item())
+        print(f"{name}: max abs err {err:.4g} (tol {tol:.3g}, ref range {y.abs().max().item():.3g})")
+        assert err < tol, f"{name}: max abs err {err} > {tol}"
+    assert torch.allclose(beta, probs / probs.sum(-1, keepdim=True), atol=1e-6)
+    assert torch.allclose(probs.sum(-1), torch.ones(B, N, device=dev), atol=1e-5)
+    # greedy = argmax of the kernel's own logits
+    assert torch.equal(greedy.long(), logits.argmax(-1))
+    # sequential mode: only agent `cur` is written, as (B,1,A)
+    cur = N - 1
+    p1 = torch.full((B, 1, A), float("nan"), device=dev)
+    b1 = torch.full((B, 1, A), float("nan"), device=dev)
+    fus.recurrent_fused(B, pool, idx, act, nxt, rew, val, p1, b1, None, None, tree_agents=1, cur=cur, inv_tau=0.5)
+    torch.cuda.synchronize()
+    assert torch.allclose(p1[:, 0], probs[:, cur], atol=1e-6)
+    bt = probs[:, cur] ** 0.5
+    assert torch.allclose(b1[:, 0], bt / bt.sum(-1, keepdim=True), atol=1e-4)

@@ -47,15 +47,16 @@ def test_step_path_reproduces_reference_known_answers(built_lib):
     check_kat(*sequential_search(fn, cfg, model, legal=kat_legal()))
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
 @pytest.mark.parametrize("cur", [None, 0, 1, 2])
-def test_device_path_replays_bit_exact_through_oracle_tree(built_lib, oracle_built, cur):
+def test_device_path_replays_bit_exact_through_oracle_tree(built_lib, oracle_built, cur, mode):
     from mazero_b200.inference import SmacInference
     from mazero_b200.mcts_sampled import SampledMCTS
 
     N, A, B, K, S = 3, 9, 48, 10, 25
     cfg = MockConfig(N, A, S, K)
     model = smac_model(N, A)
-    inf = SmacInference.from_model(model, device="cuda:0")
+    inf = SmacInference.from_model(model, device="cuda:0", mode=mode)
     out0 = root_output(model, B)
     out0 = out0._replace(hidden_state=out0.hidden_state.cuda())
     factor = np.random.RandomState(5).randint(0, A, size=(B, N)).astype(np.int32)
