@@ -77,8 +77,11 @@ class Tree_batch:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            lib.maz_tree_destroy(h)
+        if h and lib is not None:   # `lib` is None while the interpreter shuts down
+            try:
+                lib.maz_tree_destroy(h)
+            except Exception:
+                pass
             self._h = C.c_void_p()
 
     # ---- handle management (extensions; the reference builds a new object per search) -----------------
