@@ -24,7 +24,7 @@ int maz_dbg_umma_gemm(const float *a, const void *w_packed, float *out, int n, i
  * Fixed architecture (config/smac/__init__.py:15-27): hidden 128 per agent, 3 encoder layers x 8 heads,
  * dim_feedforward 128, fc_dynamic [128,128], GNN hidden 64, fc_policy [32], support 11; agents N <= 32,
  * actions A <= 48.  Weight packing: see mazero_b200/fused.py (pack_weights). */
-#define MAZ_INFER_NCHUNK 30
+#define MAZ_INFER_NCHUNK 32
 typedef struct maz_infer_desc {
     int B, N, A, KA, NAP;        /* roots, agents, actions, A rounded up to 16 (twice) */
     int Nt, cur;                 /* agents in the tree (N joint / 1 sequential), sequential agent index or -1 */
@@ -39,9 +39,12 @@ typedef struct maz_infer_desc {
     float *logits_out;           /* (B,N,A) raw policy logits, or NULL */
     const void *wpk;             /* bf16 weight chunks in tcgen05 operand layout */
     const float *vec;            /* fp32 biases / LayerNorm affine / positional table / heads */
+    int vec_floats;              /* length of vec, multiple of 4 (copied to shared memory in one bulk copy) */
     unsigned int chunk_off[MAZ_INFER_NCHUNK];
     unsigned int chunk_bytes[MAZ_INFER_NCHUNK];
     int o_bin, o_pos, o_layer, o_dyn, o_rg, o_vg, o_pol;   /* float offsets into vec */
+    long long *dbg_clock;        /* optional (NULL): SM-cycle timestamps of CTA 0's stages, 256 entries (profiling) */
+    int dbg_flags;               /* profiling only: 1 = skip the epilogue math, 2 = skip the MMAs (results are garbage) */
 } maz_infer_desc;
 
 /* replaces model.recurrent_inference + the driver's softmax/beta (mcts_sampled.py:150-161): one kernel launch */

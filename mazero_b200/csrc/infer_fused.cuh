@@ -7,10 +7,14 @@
 // Tiling: a CTA of 128 threads owns a tile of 128 token rows (thread r == row r == TMEM lane r).  A token
 // is one agent of one root; every warp holds floor(32/N) whole roots, so everything that mixes the
 // agents of a root (attention over the agent axis, the all-ones-adjacency graph sums) stays inside a warp.
-// All 30 weight matrices stream from L2 through a 3-slot shared-memory ring (1-D bulk TMA + mbarriers),
-// pre-packed on the host in the tcgen05 operand layout; every GEMM is M=128 on the tensor cores with the
-// fp32 accumulator in TMEM; the residual stream x lives in TMEM (columns 0..127) so `x + f(x)` is just an
-// accumulating MMA.  Per-row work (bias, ReLU, LayerNorm, softmax, support transform) is thread-local.
+// The 32 weight chunks (<= 32 KB each, pre-packed on the host in the tcgen05 operand layout, in consumption
+// order) stream from L2 through a 3-slot shared-memory ring (1-D bulk TMA + mbarriers); all biases /
+// LayerNorm affines / heads arrive in shared memory with one more bulk copy.  Every GEMM is M=128 on the
+// tensor cores with the fp32 accumulator in TMEM; the residual stream x lives in TMEM (columns 0..127) so
+// `x + f(x)` is an accumulating MMA.  Per-row work (bias, ReLU, LayerNorm, softmax, support transform) is
+// thread-local.  The epilogues are NON-inlined functions on purpose: the kernel is one long straight line,
+// and v1 (everything inlined, ~600 KB of SASS executed once) spent most of its time in instruction-cache
+// misses (profiles/r01_ncu_summary.md).
 #pragma once
 #include "../../include/maz_infer.h"
 #include "umma.cuh"
@@ -27,51 +31,54 @@ constexpr int GH = 64;        // GNN hidden                  (model.py:213,300 d
 constexpr int PH = 32;        // fc_policy_layers = [32]
 constexpr int SUP = 11;       // DiscreteSupport(-5, 5)
 constexpr int NLAYER = 3;     // AttentionEncoder(3, ...)    (model.py:221)
-constexpr int NCHUNK = 30;
+constexpr int NCHUNK = MAZ_INFER_NCHUNK;
 constexpr int NSLOT = 3;
+constexpr uint32_t SLOT_BYTES = 128 * 128 * 2;
 
 enum : uint32_t { TM_X = 0, TM_Q = 128, TM_K = 256, TM_V = 384, TM_ACC = 128 };
 
 using Desc = ::maz_infer_desc;
-static_assert(NCHUNK == MAZ_INFER_NCHUNK, "chunk count");
 
-__host__ __device__ inline uint32_t slot_bytes(int KA) { return 128u * (128u + (uint32_t)KA) * 2u; }
-__host__ __device__ inline size_t smem_bytes(int KA)
+__host__ __device__ inline size_t smem_bytes(int KA, int vec_floats)
 {
-    return 2 * operand_bytes(128, 128) + operand_bytes(128, KA) + NSLOT * (size_t)slot_bytes(KA) + 1024;
+    return 2 * operand_bytes(128, 128) + operand_bytes(128, KA) + NSLOT * (size_t)SLOT_BYTES + (size_t)vec_floats * 4 + 4096 + 1024;   // + row-statistics exchange
 }
 
-// ---- weight-ring producer / MMA issuer state (thread 0 only) ---------------------------------------------
-struct Issuer {
-    const Desc *d;
-    uint8_t *slots;
-    uint32_t slot_sz;
-    uint64_t *full, *empty;
-    int next_load;
-
-    __device__ __forceinline__ void load(int c)
-    {
-        const int s = c % NSLOT;
-        if (c >= NSLOT) mbar_wait(&empty[s], ((c / NSLOT) - 1) & 1);
-        mbar_expect_tx(&full[s], d->chunk_bytes[c]);
-        bulk_g2s(slots + (size_t)s * slot_sz, reinterpret_cast<const uint8_t *>(d->wpk) + d->chunk_off[c], d->chunk_bytes[c], &full[s]);
-    }
-    __device__ __forceinline__ void ensure(int upto)
-    {
-        if (upto > NCHUNK - 1) upto = NCHUNK - 1;
-        while (next_load <= upto) load(next_load++);
-    }
-    // wait until chunk c is resident; returns its shared-memory byte address
-    __device__ __forceinline__ uint32_t acquire(int c)
-    {
-        ensure(c + 2);
-        mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1);
-        tc_fence_after();
-        return smem_u32(slots + (size_t)(c % NSLOT) * slot_sz);
-    }
-    // the slot may be refilled once every MMA issued so far has completed
-    __device__ __forceinline__ void release(int c) { mma_commit(&empty[c % NSLOT]); }
+// ---- warp roles ---------------------------------------------------------------------------------------------
+// warps 0..15 : epilogue (4 TMEM lane quadrants x 4 column parts)
+// warp 16     : weight producer -- streams the 32 chunks through the 3-slot ring (bulk TMA), runs ahead freely
+// warp 17     : MMA issuer -- waits for "operands ready" (bar_ready) and "chunk resident" (bar_full), issues the
+//               tcgen05.mma's, releases ring slots (tcgen05.commit -> bar_empty) and signals bar_mma per stage
+// Keeping the single-thread, long-latency async operations (mbarrier waits, bulk copies, MMA issue, commits) on
+// their own warps takes them off the epilogue warps' critical path (v3 had thread 0 do all of it: ~2200 cycles
+// per chunk between the barrier and the MMA completion).
+struct Pipe {
+    uint64_t *full, *empty, *mma, *ready;
+    uint32_t slots;        // shared address of the ring
+    uint32_t tmem;
+    int c;                 // next chunk
+    uint32_t ready_phase;
+    int skip;              // profiling: do not issue the MMAs
 };
+
+// one weight chunk: D[dst] (+)= A[a_addr (row length a_K)] * W_c^T  (n_out columns).  MMA thread only; not inlined
+// (called 32 times; small code = warm instruction cache).
+__device__ __noinline__ void mma_chunk(Pipe &p, uint32_t dst, uint32_t a_addr, uint32_t a_K, uint32_t n_out, uint32_t accum)
+{
+    const int c = p.c, s = c % NSLOT;
+    mbar_wait(&p.full[s], (c / NSLOT) & 1);
+    tc_fence_after();
+    if (!p.skip) issue_gemm(p.tmem + dst, a_addr, a_K, 0, p.slots + (uint32_t)s * SLOT_BYTES, a_K, 0, a_K, n_out, accum != 0);
+    mma_commit(&p.empty[s]);     // slot reusable once these MMAs have completed
+    p.c = c + 1;
+}
+__device__ __noinline__ void mma_stage_begin(Pipe &p)   // all epilogue threads have published their operands
+{
+    mbar_wait(p.ready, p.ready_phase);
+    p.ready_phase ^= 1;
+    tc_fence_after();
+}
+__device__ __forceinline__ void mma_stage_end(Pipe &p) { mma_commit(p.mma); }
 
 // ---- small per-thread helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack2(float a, float b)
@@ -79,21 +86,56 @@ __device__ __forceinline__ uint32_t pack2(float a, float b)
     __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&p);
 }
-// write 16 consecutive columns [c, c+16) of row `row` into a bf16 operand tile with row length K
-__device__ __forceinline__ void store16(uint8_t *tile, int row, int c, int K, const float (&v)[16])
-{
-    uint4 a, b;
-    a.x = pack2(v[0], v[1]); a.y = pack2(v[2], v[3]); a.z = pack2(v[4], v[5]); a.w = pack2(v[6], v[7]);
-    b.x = pack2(v[8], v[9]); b.y = pack2(v[10], v[11]); b.z = pack2(v[12], v[13]); b.w = pack2(v[14], v[15]);
-    *reinterpret_cast<uint4 *>(tile + chunk_off(row, c >> 3, K)) = a;
-    *reinterpret_cast<uint4 *>(tile + chunk_off(row, (c >> 3) + 1, K)) = b;
-}
-__device__ __forceinline__ void add_vec16(float (&v)[16], const float *__restrict__ p)
+// write 16 consecutive columns [c, c+16) of row `row` into the bf16 operand tile at shared address `tile`
+template <int NV>
+__device__ __forceinline__ void store_cols(uint32_t tile, int row, int c, int K, const float (&v)[NV])
 {
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(p + i));
-        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+    for (int j = 0; j < NV; j += 8) {
+        uint4 a;
+        a.x = pack2(v[j], v[j + 1]); a.y = pack2(v[j + 2], v[j + 3]); a.z = pack2(v[j + 4], v[j + 5]); a.w = pack2(v[j + 6], v[j + 7]);
+        sts4(tile + chunk_off(row, (c + j) >> 3, K), a);
+    }
+}
+// v += vec (shared memory), with Blackwell's packed fp32 adds (FADD2)
+template <int NV>
+__device__ __forceinline__ void add_svec(float (&v)[NV], uint32_t saddr)
+{
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+        const float4 t = lds4(saddr + 4 * i);
+        const float2 a = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(t.x, t.y));
+        const float2 b = __fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(t.z, t.w));
+        v[i] = a.x; v[i + 1] = a.y; v[i + 2] = b.x; v[i + 3] = b.y;
+    }
+}
+// (sum, sumsq) of v with packed FADD2 / FFMA2
+template <int NV>
+__device__ __forceinline__ void sum_sq(const float (&v)[NV], float &sum, float &sq)
+{
+    float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NV; i += 2) {
+        const float2 x = make_float2(v[i], v[i + 1]);
+        s2 = __fadd2_rn(s2, x);
+        q2 = __ffma2_rn(x, x, q2);
+    }
+    sum = s2.x + s2.y;
+    sq = q2.x + q2.y;
+}
+// v = (v - mean) * rstd * g + b  with g, b from shared memory: a = rstd*g; v = v*a + (b - mean*a)
+template <int NV>
+__device__ __forceinline__ void ln_affine(float (&v)[NV], float mean, float rstd, uint32_t sg, uint32_t sb)
+{
+    const float2 r2 = make_float2(rstd, rstd), nm2 = make_float2(-mean, -mean);
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+        const float4 g = lds4(sg + 4 * i), b = lds4(sb + 4 * i);
+        const float2 a0 = __fmul2_rn(r2, make_float2(g.x, g.y)), a1 = __fmul2_rn(r2, make_float2(g.z, g.w));
+        const float2 c0 = __ffma2_rn(nm2, a0, make_float2(b.x, b.y)), c1 = __ffma2_rn(nm2, a1, make_float2(b.z, b.w));
+        const float2 y0 = __ffma2_rn(make_float2(v[i], v[i + 1]), a0, c0);
+        const float2 y1 = __ffma2_rn(make_float2(v[i + 2], v[i + 3]), a1, c1);
+        v[i] = y0.x; v[i + 1] = y0.y; v[i + 2] = y1.x; v[i + 3] = y1.y;
     }
 }
 
@@ -120,119 +162,378 @@ __device__ __forceinline__ float support_to_scalar(const float (&lg)[SUP])
     return out;
 }
 
-// y = LN(pre) over 128 TMEM columns starting at `tcol`, pre = acc + bias; writes fp32 to TMEM X (optional)
-// and bf16 to `tile` (K=128).  relu_after: apply ReLU after the affine (mlp()), else plain (post-LN encoder).
-__device__ __forceinline__ void ln128(uint32_t trow, uint32_t tcol, const float *__restrict__ bias, const float *__restrict__ g,
-                                      const float *__restrict__ be, bool relu_after, bool store_x, uint8_t *tile, int row)
+// ---- epilogues (one per stage kind; NOT inlined, see the header comment) ---------------------------------------
+// Thread layout of a CTA: 16 warps = 4 TMEM lane quadrants x PARTS column parts.  warp = part*4 + quad;
+// row = quad*32 + lane (a warp may only touch TMEM lanes 32*(warp%4)..+31); a thread owns the columns
+// [part*W/PARTS, (part+1)*W/PARTS) of its row in a W-wide stage.  Row statistics (LayerNorm) are combined
+// across the PARTS threads of a row through shared memory + a 128-thread named barrier per quadrant.
+constexpr int PARTS = 4;
+constexpr int NEPI = 128 * PARTS;          // epilogue threads
+constexpr int NTHREADS = NEPI + 64;        // + producer warp + MMA warp
+constexpr int CP = H / PARTS;        // 32
+constexpr int GP = GH / PARTS;       // 16
+constexpr int PP = PH / PARTS;       // 8
+constexpr int HPP = NHEAD / PARTS;   // 2
+constexpr uint32_t RED_BYTES = 128 * PARTS * 8;
+
+struct Thr {            // who am I (recomputed from threadIdx in every epilogue: cheaper than passing it around)
+    int lane, quad, part, row;
+    __device__ __forceinline__ Thr()
+    {
+        const int tid = threadIdx.x, warp = tid >> 5;
+        lane = tid & 31; quad = warp & 3; part = warp >> 2; row = quad * 32 + lane;
+    }
+};
+
+// combine (sum, sumsq) of the PARTS threads that share a row
+__device__ __forceinline__ void row_stats(const Thr &t, uint32_t aRed, float &sum, float &sq)
 {
-    float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 128; c += 16) {
-        float v[16];
-        tmem_ld16(trow + tcol + c, v);
-        add_vec16(v, bias + c);
+    sts2f(aRed + (uint32_t)(t.row * PARTS + t.part) * 8u, sum, sq);
+    named_bar_sync(1 + t.quad, 128);
+    float S = 0.f, Q = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { sum += v[i]; sq += v[i] * v[i]; }
+    for (int p = 0; p < PARTS; ++p) {
+        const float2 v = lds2f(aRed + (uint32_t)(t.row * PARTS + p) * 8u);
+        S += v.x; Q += v.y;
     }
-    const float mean = sum * (1.f / 128.f);
-    const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll 1
-    for (int c = 0; c < 128; c += 16) {
-        float v[16];
-        tmem_ld16(trow + tcol + c, v);
-        add_vec16(v, bias + c);
+    sum = S; sq = Q;
+}
+
+template <int NV>
+__device__ __forceinline__ void tmem_store_cols(uint32_t taddr, const float (&v)[NV])
+{
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float y = (v[i] - mean) * rstd * __ldg(g + c + i) + __ldg(be + c + i);
-            v[i] = relu_after ? fmaxf(y, 0.f) : y;
-        }
-        if (store_x) tmem_st16(trow + TM_X + c, v);
-        store16(tile, row, c, 128, v);
+    for (int j = 0; j < NV; j += 16) {
+        float w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = v[j + i];
+        tmem_st16(taddr + j, w);
     }
+}
+
+// x0 = relu(acc + b_in) + pos[agent]  -> TMEM X (fp32) and operand tile (bf16)
+__device__ __noinline__ void epi_inproj(uint32_t trow, uint32_t sb, uint32_t spos, uint32_t tile)
+{
+    const Thr t;
+    const int c = t.part * CP;
+    float v[CP];
+    tmem_ld32(trow + TM_ACC + c, v);
+    add_svec(v, sb + 4 * c);
+#pragma unroll
+    for (int i = 0; i < CP; i += 4) {
+        const float4 p = lds4(spos + 4 * (c + i));
+        v[i] = fmaxf(v[i], 0.f) + p.x; v[i + 1] = fmaxf(v[i + 1], 0.f) + p.y;
+        v[i + 2] = fmaxf(v[i + 2], 0.f) + p.z; v[i + 3] = fmaxf(v[i + 3], 0.f) + p.w;
+    }
+    tmem_store_cols(trow + TM_X + c, v);
+    store_cols(tile, t.row, c, H, v);
+    tmem_st_wait();
+}
+
+// f = relu(acc + b) -> operand tile
+__device__ __noinline__ void epi_bias_relu(uint32_t trow, uint32_t sb, uint32_t tile)
+{
+    const Thr t;
+    const int c = t.part * CP;
+    float v[CP];
+    tmem_ld32(trow + TM_ACC + c, v);
+    add_svec(v, sb + 4 * c);
+#pragma unroll
+    for (int i = 0; i < CP; ++i) v[i] = fmaxf(v[i], 0.f);
+    store_cols(tile, t.row, c, H, v);
+}
+
+// y = LN(acc + bias) * g + be over the 128 TMEM columns at `tcol`; optional ReLU (mlp()); optional fp32 copy
+// into the TMEM-resident residual stream X; always a bf16 copy into the operand tile.
+__device__ __noinline__ void epi_ln128(uint32_t trow, uint32_t tcol, uint32_t sb, uint32_t sg, uint32_t sbe, int relu_after,
+                                       int store_x, uint32_t tile, uint32_t aRed)
+{
+    const Thr t;
+    const int c = t.part * CP;
+    float v[CP];
+    tmem_ld32(trow + tcol + c, v);
+    add_svec(v, sb + 4 * c);
+    float sum, sq;
+    sum_sq(v, sum, sq);
+    row_stats(t, aRed, sum, sq);
+    const float mean = sum * (1.f / H);
+    const float rstd = rsqrtf(fmaxf(sq * (1.f / H) - mean * mean, 0.f) + 1e-5f);
+    ln_affine(v, mean, rstd, sg + 4 * c, sbe + 4 * c);
+    if (relu_after) {
+#pragma unroll
+        for (int i = 0; i < CP; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (store_x) tmem_store_cols(trow + TM_X + c, v);
+    store_cols(tile, t.row, c, H, v);
     if (store_x) tmem_st_wait();
 }
 
-// GraphNetNN layer (model.py:151-163) from one stacked GEMM: columns [0,64) = gc.lin(x), [64,128) = nn(x).
-// out[i] = LN(relu(sum_over_agents(gc + b_gc) + nn + b_nn)), no affine.  Result in y[64] (registers).
-__device__ __forceinline__ void gnn_layer(uint32_t trow, const float *__restrict__ bgc, const float *__restrict__ bnn, int N,
-                                          int root_lane0, float (&y)[GH])
+// scaled dot-product attention over the N agents of my root; each column part owns HPP heads; online softmax.
+// sb: shared address of [bq | bk | bv] (3 x 128 floats).  Output (bf16) into the operand tile.
+__device__ __noinline__ void epi_attention(uint32_t trow, uint32_t sb, int N, int root_lane0, uint32_t tile)
 {
-    float sum = 0.f, sq = 0.f;
+    const Thr t;
+#pragma unroll 1
+    for (int hh = t.part * HPP; hh < (t.part + 1) * HPP; ++hh) {
+        float q[16], k[16], v[16], o[16];
+        tmem_ld16(trow + TM_Q + hh * HD, q);
+        tmem_ld16(trow + TM_K + hh * HD, k);
+        tmem_ld16(trow + TM_V + hh * HD, v);
+        add_svec(q, sb + 4 * (hh * HD));
+        add_svec(k, sb + 4 * (H + hh * HD));
+        add_svec(v, sb + 4 * (2 * H + hh * HD));
 #pragma unroll
-    for (int c = 0; c < GH; c += 16) {
-        float gsum[16], g[16], nn[16];
-        tmem_ld16(trow + TM_ACC + c, g);
-        add_vec16(g, bgc + c);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) gsum[i] = 0.f;
+        for (int i = 0; i < 16; ++i) { q[i] *= 0.25f; o[i] = 0.f; }   // 1/sqrt(head_dim)
+        float m = -INFINITY, lsum = 0.f;
+#pragma unroll 1
         for (int j = 0; j < N; ++j) {
+            const int src = root_lane0 + j;
+            float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) gsum[i] += __shfl_sync(0xffffffffu, g[i], root_lane0 + j);
+            for (int i = 0; i < 16; ++i) s += q[i] * __shfl_sync(0xffffffffu, k[i], src);
+            const float mn = fmaxf(m, s);
+            const float corr = __expf(m - mn), p = __expf(s - mn);
+            lsum = lsum * corr + p;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = o[i] * corr + p * __shfl_sync(0xffffffffu, v[i], src);
+            m = mn;
         }
-        tmem_ld16(trow + TM_ACC + GH + c, nn);
-        add_vec16(nn, bnn + c);
+        const float inv = 1.f / lsum;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float t = fmaxf(gsum[i] + nn[i], 0.f);
-            y[c + i] = t;
-            sum += t;
-            sq += t * t;
+        for (int i = 0; i < 16; ++i) o[i] *= inv;
+        store_cols(tile, t.row, hh * HD, H, o);
+    }
+}
+
+// next_hidden = acc + b + hidden (fp32 residual straight from the pool); fp32 to global, bf16 to the tile
+__device__ __noinline__ void epi_next_hidden(uint32_t trow, uint32_t sb, const float *__restrict__ hrow, float *__restrict__ nh,
+                                             int valid, uint32_t tile)
+{
+    const Thr t;
+    const int c = t.part * CP;
+    float v[CP];
+    tmem_ld32(trow + TM_ACC + c, v);
+    add_svec(v, sb + 4 * c);
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < CP; i += 4) {
+            const float4 h = *reinterpret_cast<const float4 *>(hrow + c + i);
+            v[i] += h.x; v[i + 1] += h.y; v[i + 2] += h.z; v[i + 3] += h.w;
+            *reinterpret_cast<float4 *>(nh + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
     }
+    store_cols(tile, t.row, c, H, v);
+}
+
+// GraphNetNN layer (model.py:151-163) from one stacked GEMM: columns [0,64) = gc.lin(x), [64,128) = nn(x).
+// y = LN(relu(sum_over_agents(gc + b_gc) + nn + b_nn)), no affine.  sb: [b_gc | b_nn] (2 x 64 floats).
+// head == 0: y (bf16) -> operand tile (K = 64) for the second layer.
+// head == 1: mean-pool over the agents, 64 -> 11 head (V weights at sb + 128 floats, bias after), support
+//            transform; partial logits of the column parts are combined through `scratch` (shared, 24 KB);
+//            the scalar is returned by the part-0 thread of every row (0 elsewhere).
+__device__ __noinline__ float epi_gnn(uint32_t trow, uint32_t sb, int N, int root_lane0, int head, uint32_t tile, uint32_t aRed,
+                                      uint32_t scratch)
+{
+    const Thr t;
+    const int c = t.part * GP;
+    float y[GP], nn[GP];
+    {
+        float g[GP];
+        tmem_ld16(trow + TM_ACC + c, g);
+        add_svec(g, sb + 4 * c);
+#pragma unroll
+        for (int i = 0; i < GP; ++i) y[i] = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) {
+#pragma unroll
+            for (int i = 0; i < GP; ++i) y[i] += __shfl_sync(0xffffffffu, g[i], root_lane0 + j);
+        }
+    }
+    tmem_ld16(trow + TM_ACC + GH + c, nn);
+    add_svec(nn, sb + 4 * (GH + c));
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < GP; ++i) {
+        y[i] = fmaxf(y[i] + nn[i], 0.f);
+        sum += y[i];
+        sq += y[i] * y[i];
+    }
+    row_stats(t, aRed, sum, sq);
     const float mean = sum * (1.f / GH);
     const float rstd = rsqrtf(fmaxf(sq * (1.f / GH) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll
-    for (int i = 0; i < GH; ++i) y[i] = (y[i] - mean) * rstd;
-}
-
-// mean-pool over the agents of the root, then the 64 -> 11 head and the support transform
-__device__ __forceinline__ float gnn_head(float (&o)[GH], int N, int root_lane0, const float *__restrict__ Vw,
-                                          const float *__restrict__ Vb)
-{
+    for (int i = 0; i < GP; ++i) y[i] = (y[i] - mean) * rstd;
+    if (!head) {
+        store_cols(tile, t.row, c, GH, y);
+        return 0.f;
+    }
     const float invn = 1.f / (float)N;
 #pragma unroll
-    for (int i = 0; i < GH; ++i) {
+    for (int i = 0; i < GP; ++i) {
         float s = 0.f;
-        const float mine = o[i];
+        const float mine = y[i];
+#pragma unroll 1
         for (int j = 0; j < N; ++j) s += __shfl_sync(0xffffffffu, mine, root_lane0 + j);
-        o[i] = s * invn;
+        y[i] = s * invn;
     }
-    float lg[SUP];
+    const uint32_t sV = sb + 4 * (2 * GH), sVb = sV + 4 * (SUP * GH);
+    const uint32_t mine_out = scratch + (uint32_t)((t.row * PARTS + t.part) * 12) * 4u;
+#pragma unroll 1
+    for (int k = 0; k < SUP; ++k) {   // partial logits over my GP columns (rolled: executed twice per kernel)
+        float a = 0.f;
 #pragma unroll
-    for (int t = 0; t < SUP; ++t) {
-        float a = __ldg(Vb + t);
-#pragma unroll
-        for (int i = 0; i < GH; ++i) a += __ldg(Vw + t * GH + i) * o[i];
-        lg[t] = a;
+        for (int i = 0; i < GP; i += 4) {
+            const float4 w = lds4(sV + 4 * (k * GH + c + i));
+            a += w.x * y[i] + w.y * y[i + 1] + w.z * y[i + 2] + w.w * y[i + 3];
+        }
+        sts1f(mine_out + 4 * k, a);
     }
-    return support_to_scalar(lg);
+    named_bar_sync(1 + t.quad, 128);
+    if (t.part != 0) return 0.f;
+    // softmax . support -> inv_h (core/config.py:430-442, 463-499), two rolled passes over the 11 logits
+    const uint32_t rowp = scratch + (uint32_t)(t.row * PARTS * 12) * 4u;
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int k = 0; k < SUP; ++k) {
+        float a = lds1v(sVb + 4 * k);
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p) a += lds1v(rowp + (uint32_t)(p * 12 + k) * 4u);
+        sts1f(rowp + 4 * k, a);          // total logit k overwrites part 0's slot
+        m = fmaxf(m, a);
+    }
+    float ssum = 0.f, x = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < SUP; ++k) {
+        const float e = __expf(lds1v(rowp + 4 * k) - m);
+        ssum += e;
+        x += e * (float)(k - 5);
+    }
+    x /= ssum;
+    const float eps = 0.001f;
+    const float r = (sqrtf(1.f + 4.f * eps * (fabsf(x) + 1.f + eps)) - 1.f) / (2.f * eps);
+    float out = r * r - 1.f;
+    out = (x < 0.f) ? -out : out;
+    if (!(out == out)) out = 0.f;
+    if (fabsf(out) < eps) out = 0.f;
+    return out;
 }
 
-__global__ void __launch_bounds__(128, 1) k_recurrent_inference(const __grid_constant__ Desc d)
+// policy hidden: p1 = relu(LN(acc + b) * g + be) over 32 columns -> operand tile (K = 32)
+__device__ __noinline__ void epi_policy_hidden(uint32_t trow, uint32_t sp, uint32_t tile, uint32_t aRed)
+{
+    const Thr t;
+    const int c = t.part * PP;
+    float p[PP];
+    tmem_ld8(trow + TM_ACC + c, p);
+    add_svec(p, sp + 4 * c);
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < PP; ++i) { sum += p[i]; sq += p[i] * p[i]; }
+    row_stats(t, aRed, sum, sq);
+    const float mean = sum * (1.f / PH);
+    const float rstd = rsqrtf(fmaxf(sq * (1.f / PH) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < PP; i += 4) {
+        const float4 g = lds4(sp + 4 * (PH + c + i)), b = lds4(sp + 4 * (2 * PH + c + i));
+        p[i] = fmaxf((p[i] - mean) * rstd * g.x + b.x, 0.f); p[i + 1] = fmaxf((p[i + 1] - mean) * rstd * g.y + b.y, 0.f);
+        p[i + 2] = fmaxf((p[i + 2] - mean) * rstd * g.z + b.z, 0.f); p[i + 3] = fmaxf((p[i + 3] - mean) * rstd * g.w + b.w, 0.f);
+    }
+    store_cols(tile, t.row, c, PH, p);
+}
+
+// policy logits -> softmax -> probs, beta = probs^(1/tau) renormalised (mcts_sampled.py:158-161), greedy action.
+// Executed by the part-0 warps only (A <= 48 columns), as three rolled passes over 16-column TMEM chunks
+// (small code: this runs once per kernel, see issue_chunk's note on instruction fetch).
+__device__ __noinline__ void epi_policy_out(const Desc &d, uint32_t trow, uint32_t sb2, int valid, int root, int agent)
+{
+    const int A = d.A, NAP = d.NAP;
+    float m = -INFINITY;
+    int am = 0;
+#pragma unroll 1
+    for (int cc = 0; cc < NAP; cc += 16) {
+        float v[16];
+        tmem_ld16(trow + TM_ACC + cc, v);
+        add_svec(v, sb2 + 4 * cc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (cc + i < A && v[i] > m) { m = v[i]; am = cc + i; }
+        if (valid && d.logits_out) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (cc + i < A) d.logits_out[((size_t)root * d.N + agent) * A + cc + i] = v[i];
+        }
+    }
+    const int ta = (d.cur < 0) ? agent : (agent == d.cur ? 0 : -1);
+    const bool unit_tau = (d.inv_tau == 1.0f);
+    float s = 0.f, sbeta = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < NAP; cc += 16) {
+        float v[16];
+        tmem_ld16(trow + TM_ACC + cc, v);
+        add_svec(v, sb2 + 4 * cc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float e = (cc + i < A) ? __expf(v[i] - m) : 0.f;
+            s += e;
+            sbeta += unit_tau ? e : ((cc + i < A) ? __powf(e, d.inv_tau) : 0.f);   // (e/s)^t = e^t / s^t
+        }
+    }
+    if (valid && d.greedy) d.greedy[(size_t)root * d.N + agent] = am;
+    // NOTE: no early return before the last tcgen05.ld: it is warp-collective (.sync.aligned), every lane of the
+    // warp must execute it; only the stores are predicated.
+    const bool writer = valid && ta >= 0;
+    const float invs = 1.f / s, invb = 1.f / sbeta;
+    float *po = d.probs + (writer ? ((size_t)root * d.Nt + ta) * A : 0);
+    float *bo = d.beta + (writer ? ((size_t)root * d.Nt + ta) * A : 0);
+#pragma unroll 1
+    for (int cc = 0; cc < NAP; cc += 16) {
+        float v[16];
+        tmem_ld16(trow + TM_ACC + cc, v);
+        add_svec(v, sb2 + 4 * cc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (writer && cc + i < A) {
+                const float e = __expf(v[i] - m);
+                po[cc + i] = e * invs;
+                bo[cc + i] = (unit_tau ? e : __powf(e, d.inv_tau)) * invb;
+            }
+    }
+}
+
+// fp32 pool row -> bf16 operand tile (K = 128), my 32 columns
+__device__ __noinline__ void gather_hidden(const float *__restrict__ hrow, int valid, uint32_t tile)
+{
+    const Thr t;
+    const int c = t.part * CP;
+    float v[CP];
+#pragma unroll
+    for (int i = 0; i < CP; i += 4) {
+        const float4 h = valid ? *reinterpret_cast<const float4 *>(hrow + c + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = h.x; v[i + 1] = h.y; v[i + 2] = h.z; v[i + 3] = h.w;
+    }
+    store_cols(tile, t.row, c, H, v);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __grid_constant__ Desc d)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_mma;
+    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_mma, bar_ready, bar_vec;
     __shared__ uint32_t tmem_base_s;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = d.N, A = d.A, KA = d.KA;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int N = d.N, KA = d.KA;
     uint8_t *sX = smem;                               // 128 x 128 bf16
     uint8_t *sT = sX + operand_bytes(128, 128);       // 128 x 128 bf16
     uint8_t *sOne = sT + operand_bytes(128, 128);     // 128 x KA  bf16 (one-hot joint action)
-    uint8_t *sW = sOne + operand_bytes(128, KA);      // weight ring
-    const uint32_t slot_sz = slot_bytes(KA);
-
-    // token <-> (root, agent)
-    const int rpw = 32 / N;                           // whole roots per warp
-    const int rl = lane / N, agent = lane - rl * N;
-    const int root = (blockIdx.x * 4 + warp) * rpw + rl;
-    const bool valid = (rl < rpw) && (root < d.B);
-    const int root_lane0 = (rl < rpw) ? rl * N : 0;   // first lane of my root inside the warp
-    const int row = tid;
+    uint8_t *sW = sOne + operand_bytes(128, KA);      // weight ring, NSLOT x 32 KB
+    uint8_t *sR = sW + NSLOT * (size_t)SLOT_BYTES;    // row-statistics exchange, 4 KB
+    uint8_t *sP = sR + RED_BYTES;                     // fp32 parameters (d.vec)
 
     if (tid == 0) {
         for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         mbar_init(&bar_mma, 1);
+        mbar_init(&bar_ready, 1);
+        mbar_init(&bar_vec, 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -240,385 +541,180 @@ __global__ void __launch_bounds__(128, 1) k_recurrent_inference(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    const uint32_t aX = smem_u32(sX), aT = smem_u32(sT), aOne = smem_u32(sOne), aP = smem_u32(sP), aRed = smem_u32(sR);
 
-    Issuer is{&d, sW, slot_sz, bar_full, bar_empty, 0};
-    if (tid == 0) is.ensure(NSLOT - 1);               // start streaming the first weight chunks
-    uint32_t mma_phase = 0;
-    const uint32_t aX = smem_u32(sX), aT = smem_u32(sT), aOne = smem_u32(sOne);
-
-    // ---- gather the parent's hidden state and build the one-hot action operand ----------------------------
-    const float *hrow = nullptr;
-    int my_action = 0;
-    if (valid) {
-        const int ix = d.idx_x ? d.idx_x[root] : 0;
-        hrow = d.pool + ((size_t)ix * d.B + root) * (size_t)(N * H) + (size_t)agent * H;
-        my_action = d.actions[(size_t)root * N + agent];
-    }
-    auto gather_h = [&]() {
-#pragma unroll 4
-        for (int c = 0; c < H; c += 16) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-                float4 t = valid ? *reinterpret_cast<const float4 *>(hrow + c + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    if (warp == NEPI / 32) {
+        // ================================ weight producer =====================================================
+        if ((tid & 31) == 0) {
+            mbar_expect_tx(&bar_vec, (uint32_t)d.vec_floats * 4u);
+            bulk_g2s(sP, d.vec, (uint32_t)d.vec_floats * 4u, &bar_vec);
+#pragma unroll 1
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int s = c % NSLOT;
+                if (c >= NSLOT) mbar_wait_backoff(&bar_empty[s], ((c / NSLOT) - 1) & 1);
+                const uint32_t nbytes = (d.dbg_flags & 4) ? 16u : d.chunk_bytes[c];   // profiling: tiny copies
+                mbar_expect_tx(&bar_full[s], nbytes);
+                bulk_g2s(sW + (size_t)s * SLOT_BYTES, reinterpret_cast<const uint8_t *>(d.wpk) + d.chunk_off[c], nbytes, &bar_full[s]);
             }
-            store16(sT, row, c, H, v);
         }
-    };
-    gather_h();
-    for (int c = 0; c < KA; c += 16) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (valid && (c + i) == my_action) ? 1.f : 0.f;
-        store16(sOne, row, c, KA, v);
-    }
-
-#define STAGE_SYNC()          \
-    fence_proxy_async();      \
-    tc_fence_before();        \
-    __syncthreads();
-#define WAIT_MMA()                 \
+    } else if (warp == NEPI / 32 + 1) {
+        // ================================ MMA issuer ==========================================================
+        if ((tid & 31) == 0) {
+            Pipe p{bar_full, bar_empty, &bar_mma, &bar_ready, smem_u32(sW), tmem, 0, 0, (d.dbg_flags & 2)};
+            const uint32_t uKA = (uint32_t)KA;
+            mma_stage_begin(p);                                   // in-proj: W_in [h | onehot]
+            mma_chunk(p, TM_ACC, aT, H, 128, 0);
+            mma_chunk(p, TM_ACC, aOne, uKA, 128, 1);
+            mma_stage_end(p);
+#pragma unroll 1
+            for (int l = 0; l < NLAYER; ++l) {
+                mma_stage_begin(p);                               // q, k, v projections
+                mma_chunk(p, TM_Q, aX, H, 128, 0);
+                mma_chunk(p, TM_K, aX, H, 128, 0);
+                mma_chunk(p, TM_V, aX, H, 128, 0);
+                mma_stage_end(p);
+                mma_stage_begin(p);                               // x += sa Wo^T (residual = accumulate into X)
+                mma_chunk(p, TM_X, aT, H, 128, 1);
+                mma_stage_end(p);
+                mma_stage_begin(p);                               // linear1
+                mma_chunk(p, TM_ACC, aX, H, 128, 0);
+                mma_stage_end(p);
+                mma_stage_begin(p);                               // x += f W2^T
+                mma_chunk(p, TM_X, aT, H, 128, 1);
+                mma_stage_end(p);
+            }
+            mma_stage_begin(p);                                   // fc_dynamic.0 on [h | onehot | attn]
+            mma_chunk(p, TM_ACC, aT, H, 128, 0);
+            mma_chunk(p, TM_ACC, aOne, uKA, 128, 1);
+            mma_chunk(p, TM_ACC, aX, H, 128, 1);
+            mma_stage_end(p);
+            mma_stage_begin(p);
+            mma_chunk(p, TM_ACC, aT, H, 128, 0);                  // fc_dynamic.3
+            mma_stage_end(p);
+            mma_stage_begin(p);
+            mma_chunk(p, TM_ACC, aX, H, 128, 0);                  // fc_dynamic.6
+            mma_stage_end(p);
+            mma_stage_begin(p);                                   // reward GNN layer 1 on [h' | onehot]
+            mma_chunk(p, TM_ACC, aT, H, 128, 0);
+            mma_chunk(p, TM_ACC, aOne, uKA, 128, 1);
+            mma_stage_end(p);
+            mma_stage_begin(p);
+            mma_chunk(p, TM_ACC, aX, GH, 128, 0);                 // reward GNN layer 2
+            mma_stage_end(p);
+            mma_stage_begin(p);
+            mma_chunk(p, TM_ACC, aT, H, 128, 0);                  // value GNN layer 1
+            mma_stage_end(p);
+            mma_stage_begin(p);
+            mma_chunk(p, TM_ACC, aX, GH, 128, 0);                 // value GNN layer 2
+            mma_stage_end(p);
+            mma_stage_begin(p);
+            mma_chunk(p, TM_ACC, aT, H, PH, 0);                   // fc_policy.0
+            mma_stage_end(p);
+            mma_stage_begin(p);
+            mma_chunk(p, TM_ACC, aX, PH, (uint32_t)d.NAP, 0);     // fc_policy.3
+            mma_stage_end(p);
+        }
+    } else {
+        // ================================ epilogue warps ======================================================
+        const Thr t;
+        const uint32_t trow = tmem + ((uint32_t)(t.quad * 32) << 16);   // this warp's 32 TMEM lanes
+        // token <-> (root, agent): every quadrant-warp holds floor(32/N) whole roots
+        const int rpw = 32 / N;
+        const int rl = t.lane / N, agent = t.lane - rl * N;
+        const int root = (blockIdx.x * 4 + t.quad) * rpw + rl;
+        const int valid = (rl < rpw) && (root < d.B);
+        const int root_lane0 = (rl < rpw) ? rl * N : 0;   // first lane of my root inside the warp
+        uint32_t mma_phase = 0;
+        const bool do_epi = !(d.dbg_flags & 1);
+        int ts_n = 0;
+        const bool ts_on = d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0;
+#define TS() \
+    if (ts_on && ts_n < 256) d.dbg_clock[ts_n++] = clock64();
+// publish my operand writes to the async proxy, tell the MMA warp, wait for the stage's accumulator
+#define HANDOFF()                   \
+    TS();                           \
+    fence_proxy_async();            \
+    tc_fence_before();              \
+    named_bar_sync(5, NEPI);        \
+    if (tid == 0) mbar_arrive(&bar_ready); \
     mbar_wait(&bar_mma, mma_phase); \
     mma_phase ^= 1;                 \
-    tc_fence_after();
+    tc_fence_after();               \
+    TS();
 
-    int c = 0;  // next weight chunk (all threads track it; only thread 0 uses it)
-    const float *vec = d.vec;
-
-    // ---- attention_stack[0..1]: x0 = relu(W_in [h | onehot] + b) (+ positional table) ----------------------
-    STAGE_SYNC();
-    if (tid == 0) {
-        const uint32_t w = is.acquire(c);
-        issue_gemm(tmem + TM_ACC, aT, H, 0, w, H + KA, 0, H, 128, false);
-        issue_gemm(tmem + TM_ACC, aOne, KA, 0, w, H + KA, H, KA, 128, true);
-        is.release(c);
-        mma_commit(&bar_mma);
-    }
-    ++c;
-    WAIT_MMA();
-    {
-        const float *pos = vec + d.o_pos + agent * H;
-#pragma unroll 1
-        for (int cc = 0; cc < H; cc += 16) {
-            float v[16];
-            tmem_ld16(trow + TM_ACC + cc, v);
-            add_vec16(v, vec + d.o_bin + cc);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f) + __ldg(pos + cc + i);
-            tmem_st16(trow + TM_X + cc, v);
-            store16(sX, row, cc, H, v);
-        }
-        tmem_st_wait();
-    }
-
-    // ---- 3 x post-LN TransformerEncoderLayer over the agent axis (attention.py:36-43) ------------------------
-#pragma unroll 1
-    for (int l = 0; l < NLAYER; ++l) {
-        const float *lv = vec + d.o_layer + l * 1280;
-        const float *bq = lv, *bk = lv + 128, *bv = lv + 256, *bo = lv + 384, *g1 = lv + 512, *be1 = lv + 640;
-        const float *b1 = lv + 768, *b2 = lv + 896, *g2 = lv + 1024, *be2 = lv + 1152;
-        STAGE_SYNC();
-        if (tid == 0) {
-            for (int p = 0; p < 3; ++p) {  // q, k, v projections into three TMEM regions
-                const uint32_t w = is.acquire(c + p);
-                issue_gemm(tmem + TM_Q + 128 * p, aX, H, 0, w, H, 0, H, 128, false);
-                is.release(c + p);
-            }
-            mma_commit(&bar_mma);
-        }
-        c += 3;
-        WAIT_MMA();
-        // scaled dot-product attention, one head at a time, online softmax over the N agents of my root
-#pragma unroll 1
-        for (int hh = 0; hh < NHEAD; ++hh) {
-            float q[16], k[16], v[16], o[16];
-            tmem_ld16(trow + TM_Q + hh * HD, q);
-            tmem_ld16(trow + TM_K + hh * HD, k);
-            tmem_ld16(trow + TM_V + hh * HD, v);
-            add_vec16(q, bq + hh * HD);
-            add_vec16(k, bk + hh * HD);
-            add_vec16(v, bv + hh * HD);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { q[i] *= 0.25f; o[i] = 0.f; }
-            float m = -INFINITY, lsum = 0.f;
-            for (int j = 0; j < N; ++j) {
-                const int src = root_lane0 + j;
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) s += q[i] * __shfl_sync(0xffffffffu, k[i], src);
-                const float mn = fmaxf(m, s);
-                const float corr = __expf(m - mn), p = __expf(s - mn);
-                lsum = lsum * corr + p;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = o[i] * corr + p * __shfl_sync(0xffffffffu, v[i], src);
-                m = mn;
-            }
-            const float inv = 1.f / lsum;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] *= inv;
-            store16(sT, row, hh * HD, H, o);
-        }
-        STAGE_SYNC();
-        if (tid == 0) {  // x += sa Wo^T   (residual add = accumulate into the TMEM-resident stream)
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_X, aT, H, 0, w, H, 0, H, 128, true);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        ln128(trow, TM_X, bo, g1, be1, false, true, sX, row);   // norm1
-        STAGE_SYNC();
-        if (tid == 0) {
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aX, H, 0, w, H, 0, H, 128, false);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-#pragma unroll 1
-        for (int cc = 0; cc < H; cc += 16) {  // f = relu(x W1^T + b1)
-            float v[16];
-            tmem_ld16(trow + TM_ACC + cc, v);
-            add_vec16(v, b1 + cc);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-            store16(sT, row, cc, H, v);
-        }
-        STAGE_SYNC();
-        if (tid == 0) {  // x += f W2^T
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_X, aT, H, 0, w, H, 0, H, 128, true);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        ln128(trow, TM_X, b2, g2, be2, false, true, sX, row);   // norm2
-    }
-
-    // ---- fc_dynamic on [h | onehot | attn]: Linear-LN-ReLU, Linear-LN-ReLU, Linear; residual (model.py:262-268)
-    {
-        const float *dv = vec + d.o_dyn;
-        gather_h();   // h (bf16) back into sT; sX holds the attention output
-        STAGE_SYNC();
-        if (tid == 0) {
-            uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aT, H, 0, w, H, 0, H, 128, false);
-            is.release(c);
-            w = is.acquire(c + 1);
-            issue_gemm(tmem + TM_ACC, aOne, KA, 0, w, KA, 0, KA, 128, true);
-            is.release(c + 1);
-            w = is.acquire(c + 2);
-            issue_gemm(tmem + TM_ACC, aX, H, 0, w, H, 0, H, 128, true);
-            is.release(c + 2);
-            mma_commit(&bar_mma);
-        }
-        c += 3;
-        WAIT_MMA();
-        ln128(trow, TM_ACC, dv, dv + 128, dv + 256, true, false, sT, row);
-        STAGE_SYNC();
-        if (tid == 0) {
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aT, H, 0, w, H, 0, H, 128, false);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        ln128(trow, TM_ACC, dv + 384, dv + 512, dv + 640, true, false, sX, row);
-        STAGE_SYNC();
-        if (tid == 0) {
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aX, H, 0, w, H, 0, H, 128, false);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        float *nh = valid ? d.next_hidden + (size_t)root * (N * H) + (size_t)agent * H : nullptr;
-#pragma unroll 1
-        for (int cc = 0; cc < H; cc += 16) {  // next_hidden = update + hidden  (fp32 residual from the pool)
-            float v[16];
-            tmem_ld16(trow + TM_ACC + cc, v);
-            add_vec16(v, dv + 768 + cc);
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 t = *reinterpret_cast<const float4 *>(hrow + cc + i);
-                    v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-                    *reinterpret_cast<float4 *>(nh + cc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                }
-            }
-            store16(sT, row, cc, H, v);
-        }
-    }
-
-    // ---- reward head: GraphNetNN on [next_hidden | onehot] (model.py:270-277) ----------------------------------
-    {
-        const float *rv = vec + d.o_rg;
-        float y[GH];
-        STAGE_SYNC();
-        if (tid == 0) {
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aT, H, 0, w, H + KA, 0, H, 128, false);
-            issue_gemm(tmem + TM_ACC, aOne, KA, 0, w, H + KA, H, KA, 128, true);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        gnn_layer(trow, rv, rv + 64, N, root_lane0, y);
-#pragma unroll
-        for (int cc = 0; cc < GH; cc += 16) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = y[cc + i];
-            store16(sX, row, cc, GH, v);
-        }
-        STAGE_SYNC();
-        if (tid == 0) {
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aX, GH, 0, w, GH, 0, GH, 128, false);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        gnn_layer(trow, rv + 128, rv + 192, N, root_lane0, y);
-        const float r = gnn_head(y, N, root_lane0, rv + 256, rv + 256 + SUP * GH);
-        if (valid && agent == 0) d.reward[root] = r;
-    }
-    // ---- value head: GraphNetNN on next_hidden (model.py:359) ---------------------------------------------------
-    {
-        const float *vv = vec + d.o_vg;
-        float y[GH];
-        STAGE_SYNC();
-        if (tid == 0) {
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aT, H, 0, w, H, 0, H, 128, false);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        gnn_layer(trow, vv, vv + 64, N, root_lane0, y);
-#pragma unroll
-        for (int cc = 0; cc < GH; cc += 16) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = y[cc + i];
-            store16(sX, row, cc, GH, v);
-        }
-        STAGE_SYNC();
-        if (tid == 0) {
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aX, GH, 0, w, GH, 0, GH, 128, false);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        gnn_layer(trow, vv + 128, vv + 192, N, root_lane0, y);
-        const float val = gnn_head(y, N, root_lane0, vv + 256, vv + 256 + SUP * GH);
-        if (valid && agent == 0) d.value[root] = val;
-    }
-    // ---- policy head: Linear(128,32)-LN-ReLU-Linear(32,A) per agent, then the driver's softmax / beta --------------
-    {
-        const float *pv = vec + d.o_pol;
-        STAGE_SYNC();
-        if (tid == 0) {
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aT, H, 0, w, H, 0, H, PH, false);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        {
-            float p[PH];
-            float sum = 0.f, sq = 0.f;
-#pragma unroll
-            for (int cc = 0; cc < PH; cc += 16) {
-                float v[16];
-                tmem_ld16(trow + TM_ACC + cc, v);
-                add_vec16(v, pv + cc);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { p[cc + i] = v[i]; sum += v[i]; sq += v[i] * v[i]; }
-            }
-            const float mean = sum * (1.f / PH);
-            const float rstd = rsqrtf(fmaxf(sq * (1.f / PH) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll
-            for (int cc = 0; cc < PH; cc += 16) {
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    v[i] = fmaxf((p[cc + i] - mean) * rstd * __ldg(pv + 32 + cc + i) + __ldg(pv + 64 + cc + i), 0.f);
-                store16(sX, row, cc, PH, v);
-            }
-        }
-        STAGE_SYNC();
-        if (tid == 0) {
-            const uint32_t w = is.acquire(c);
-            issue_gemm(tmem + TM_ACC, aX, PH, 0, w, PH, 0, PH, d.NAP, false);
-            is.release(c);
-            mma_commit(&bar_mma);
-        }
-        ++c;
-        WAIT_MMA();
-        float lg[48];
-#pragma unroll
-        for (int cc = 0; cc < 48; cc += 16) {
-            float v[16];
-            if (cc < d.NAP) {
-                tmem_ld16(trow + TM_ACC + cc, v);
-                add_vec16(v, pv + 96 + cc);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) lg[cc + i] = (cc < d.NAP && cc + i < A) ? v[i] : -INFINITY;
-        }
+        // ---- gather the parent's hidden state and build the one-hot action operand ------------------------
+        const float *hrow = d.pool;
+        int my_action = -1;
         if (valid) {
-            float m = -INFINITY;
-            int am = 0;
-#pragma unroll
-            for (int a = 0; a < 48; ++a)
-                if (lg[a] > m) { m = lg[a]; am = a; }
-            if (d.greedy) d.greedy[(size_t)root * N + agent] = am;
-            if (d.logits_out) {
-#pragma unroll
-                for (int a = 0; a < 48; ++a)
-                    if (a < A) d.logits_out[((size_t)root * N + agent) * A + a] = lg[a];
-            }
-            const int ta = (d.cur < 0) ? agent : (agent == d.cur ? 0 : -1);
-            if (ta >= 0) {
-                float s = 0.f, sb = 0.f;
-                float pr[48];
-#pragma unroll
-                for (int a = 0; a < 48; ++a) { pr[a] = __expf(lg[a] - m); s += pr[a]; }
-                const float invs = 1.f / s;
-                const bool unit_tau = (d.inv_tau == 1.0f);
-#pragma unroll
-                for (int a = 0; a < 48; ++a) {
-                    pr[a] *= invs;
-                    sb += unit_tau ? pr[a] : ((a < A) ? __powf(pr[a], d.inv_tau) : 0.f);
-                }
-                const float invb = 1.f / sb;
-                float *po = d.probs + ((size_t)root * d.Nt + ta) * A;
-                float *bo_ = d.beta + ((size_t)root * d.Nt + ta) * A;
-#pragma unroll
-                for (int a = 0; a < 48; ++a)
-                    if (a < A) {
-                        po[a] = pr[a];
-                        bo_[a] = (unit_tau ? pr[a] : __powf(pr[a], d.inv_tau)) * invb;
-                    }
-            }
+            const int ix = d.idx_x ? d.idx_x[root] : 0;
+            hrow = d.pool + ((size_t)ix * d.B + root) * (size_t)(N * H) + (size_t)agent * H;
+            my_action = d.actions[(size_t)root * N + agent];
         }
+        gather_hidden(hrow, valid, aT);
+        if (t.part * 16 < KA) {
+            const int c0 = t.part * 16;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = ((c0 + i) == my_action) ? 1.f : 0.f;
+            store_cols(aOne, t.row, c0, KA, v);
+        }
+        mbar_wait(&bar_vec, 0);   // parameters resident
+        // ---- attention_stack[0..1]: x0 = relu(W_in [h | onehot] + b) + positional table --------------------
+        HANDOFF();
+        if (do_epi) epi_inproj(trow, aP + 4 * d.o_bin, aP + 4 * (d.o_pos + agent * H), aX);
+        // ---- 3 x post-LN TransformerEncoderLayer over the agent axis (attention.py:36-43) ---------------------
+#pragma unroll 1
+        for (int l = 0; l < NLAYER; ++l) {
+            const uint32_t lv = aP + 4 * (d.o_layer + l * 1280);   // bq bk bv bo g1 be1 b1 b2 g2 be2
+            HANDOFF();
+            if (do_epi) epi_attention(trow, lv, N, root_lane0, aT);
+            HANDOFF();
+            if (do_epi) epi_ln128(trow, TM_X, lv + 4 * 384, lv + 4 * 512, lv + 4 * 640, 0, 1, aX, aRed);     // norm1
+            HANDOFF();
+            if (do_epi) epi_bias_relu(trow, lv + 4 * 768, aT);                                                 // relu(linear1)
+            HANDOFF();
+            if (do_epi) epi_ln128(trow, TM_X, lv + 4 * 896, lv + 4 * 1024, lv + 4 * 1152, 0, 1, aX, aRed);   // norm2
+        }
+        // ---- fc_dynamic: Linear-LN-ReLU, Linear-LN-ReLU, Linear; residual (model.py:262-268) ------------------
+        const uint32_t dv = aP + 4 * d.o_dyn;
+        gather_hidden(hrow, valid, aT);   // h (bf16) back into sT; sX holds the attention output
+        HANDOFF();
+        if (do_epi) epi_ln128(trow, TM_ACC, dv, dv + 4 * 128, dv + 4 * 256, 1, 0, aT, aRed);
+        HANDOFF();
+        if (do_epi) epi_ln128(trow, TM_ACC, dv + 4 * 384, dv + 4 * 512, dv + 4 * 640, 1, 0, aX, aRed);
+        HANDOFF();
+        {
+            float *nh = d.next_hidden + (valid ? (size_t)root * (N * H) + (size_t)agent * H : 0);
+            if (do_epi) epi_next_hidden(trow, dv + 4 * 768, hrow, nh, valid, aT);
+        }
+        // ---- reward head: GraphNetNN on [next_hidden | onehot] (model.py:270-277) -----------------------------
+        const uint32_t rv = aP + 4 * d.o_rg;
+        HANDOFF();
+        if (do_epi) epi_gnn(trow, rv, N, root_lane0, 0, aX, aRed, 0);
+        HANDOFF();
+        {
+            const float r = !do_epi ? 0.f : epi_gnn(trow, rv + 4 * 128, N, root_lane0, 1, 0, aRed, aX);   // sX is free: scratch
+            if (valid && agent == 0 && t.part == 0) d.reward[root] = r;
+        }
+        // ---- value head: GraphNetNN on next_hidden (model.py:359) ----------------------------------------------
+        const uint32_t vv = aP + 4 * d.o_vg;
+        HANDOFF();
+        if (do_epi) epi_gnn(trow, vv, N, root_lane0, 0, aX, aRed, 0);
+        HANDOFF();
+        {
+            const float val = !do_epi ? 0.f : epi_gnn(trow, vv + 4 * 128, N, root_lane0, 1, 0, aRed, aX);
+            if (valid && agent == 0 && t.part == 0) d.value[root] = val;
+        }
+        // ---- policy head + the driver's softmax / beta ------------------------------------------------------------
+        const uint32_t pv = aP + 4 * d.o_pol;
+        HANDOFF();
+        if (do_epi) epi_policy_hidden(trow, pv, aX, aRed);
+        HANDOFF();
+        if (do_epi && t.part == 0) epi_policy_out(d, trow, pv + 4 * 96, valid, root, agent);
+        TS();
+#undef HANDOFF
+#undef TS
     }
-#undef STAGE_SYNC
-#undef WAIT_MMA
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);

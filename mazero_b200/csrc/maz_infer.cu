@@ -97,7 +97,9 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
         return set_last_error(3, "maz_infer_recurrent: unsupported shape (agents <= 32, actions <= 48)");
     if (!d->pool || !d->actions || !d->next_hidden || !d->reward || !d->value || !d->probs || !d->beta || !d->wpk || !d->vec)
         return set_last_error(1, "maz_infer_recurrent: NULL tensor");
-    const size_t dyn = fused::smem_bytes(d->KA);
+    if (d->vec_floats <= 0 || d->vec_floats % 4) return set_last_error(1, "maz_infer_recurrent: vec_floats must be a positive multiple of 4");
+    const size_t dyn = fused::smem_bytes(d->KA, d->vec_floats);
+    if (dyn > 227 * 1024) return set_last_error(3, "maz_infer_recurrent: parameters do not fit in shared memory");
     static size_t configured = 0;
     if (dyn > configured) {
         cudaError_t e = cudaFuncSetAttribute(fused::k_recurrent_inference, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -106,7 +108,7 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
     }
     const int roots_per_tile = 4 * (32 / d->N);
     const int tiles = (d->B + roots_per_tile - 1) / roots_per_tile;
-    fused::k_recurrent_inference<<<tiles, 128, dyn, static_cast<cudaStream_t>(stream)>>>(*d);
+    fused::k_recurrent_inference<<<tiles, fused::NTHREADS, dyn, static_cast<cudaStream_t>(stream)>>>(*d);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_last_error(2, std::string("k_recurrent_inference: ") + cudaGetErrorString(e));
     return 0;

@@ -27,6 +27,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
@@ -103,7 +107,9 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---- TMEM <-> registers: 32 lanes x 32-bit, 16 consecutive columns per call ------------------------------
+// ---- TMEM <-> registers: 32 lanes x 32-bit, 16 / 32 consecutive columns per call -------------------------
+// The loaded registers are passed THROUGH the wait statement ("+r") so that neither nvcc nor ptxas can
+// schedule a consumer between the asynchronous load and tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 {
     uint32_t r[16];
@@ -113,9 +119,91 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// named barrier over `nthreads` threads (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void sts2f(uint32_t saddr, float a, float b)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(saddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float2 lds2f(uint32_t saddr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts1f(uint32_t saddr, float a)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(a) : "memory");
+}
+__device__ __forceinline__ float lds1v(uint32_t saddr)   // volatile-ordered scalar load (exchange buffers)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+// shared-space vector load / store with 32-bit shared addresses
+__device__ __forceinline__ float4 lds4(uint32_t saddr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float lds1(uint32_t saddr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t saddr, uint4 v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16])
 {
@@ -146,11 +234,23 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uin
                                            uint32_t w_K, uint32_t w_k0, uint32_t kk, uint32_t N, bool accumulate)
 {
     const uint32_t idesc = instr_desc_bf16(128, N);
+    // descriptors of consecutive K=16 steps differ only in the start-address field: +256 B = +16 (address >> 4)
+    uint64_t da = smem_desc(a_addr + (a_k0 >> 3) * kLBO, kLBO, sbo_bytes(a_K));
+    uint64_t db = smem_desc(w_addr + (w_k0 >> 3) * kLBO, kLBO, sbo_bytes(w_K));
+    uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll 1
     for (uint32_t k = 0; k < kk; k += 16) {
-        const uint64_t da = smem_desc(a_addr + ((a_k0 + k) >> 3) * kLBO, kLBO, sbo_bytes(a_K));
-        const uint64_t db = smem_desc(w_addr + ((w_k0 + k) >> 3) * kLBO, kLBO, sbo_bytes(w_K));
-        mma_bf16(d_tmem, da, db, idesc, (accumulate || k > 0) ? 1u : 0u);
+        mma_bf16(d_tmem, da, db, idesc, acc);
+        da += 16;
+        db += 16;
+        acc = 1u;
     }
+}
+// polling wait with back-off, for the single-thread producer / MMA warps (keeps them out of the epilogue
+// warps' issue slots and shared-memory pipe while they wait)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(32);
 }
 
 }  // namespace umma

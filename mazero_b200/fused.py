@@ -9,7 +9,7 @@ import torch
 
 from ._lib import check, lib
 
-NCHUNK = 30
+NCHUNK = 32
 H, GH, PH, SUP = 128, 64, 32, 11
 
 
@@ -19,10 +19,10 @@ class InferDesc(C.Structure):
         ("inv_tau", C.c_float),
         ("pool", C.c_void_p), ("idx_x", C.c_void_p), ("actions", C.c_void_p), ("next_hidden", C.c_void_p),
         ("reward", C.c_void_p), ("value", C.c_void_p), ("probs", C.c_void_p), ("beta", C.c_void_p), ("greedy", C.c_void_p),
-        ("logits_out", C.c_void_p), ("wpk", C.c_void_p), ("vec", C.c_void_p),
+        ("logits_out", C.c_void_p), ("wpk", C.c_void_p), ("vec", C.c_void_p), ("vec_floats", C.c_int),
         ("chunk_off", C.c_uint * NCHUNK), ("chunk_bytes", C.c_uint * NCHUNK),
         ("o_bin", C.c_int), ("o_pos", C.c_int), ("o_layer", C.c_int), ("o_dyn", C.c_int), ("o_rg", C.c_int),
-        ("o_vg", C.c_int), ("o_pol", C.c_int),
+        ("o_vg", C.c_int), ("o_pol", C.c_int), ("dbg_clock", C.c_void_p), ("dbg_flags", C.c_int),
     ]
 
 
@@ -84,7 +84,7 @@ class FusedParams:
         d, p = "dynamics_network.", "prediction_network."
         chunks = []
         w_in = g(d + "attention_stack.0.weight")                       # (128, 128 + A)
-        chunks.append(_padcols(w_in, H + KA))
+        chunks += [w_in[:, :H], _padcols(w_in[:, H:H + A], KA)]
         for l in range(3):
             e = f"{d}attention_stack.2.encoder.layers.{l}."
             qkv = g(e + "self_attn.in_proj_weight")
@@ -94,7 +94,8 @@ class FusedParams:
         chunks += [wd1[:, :H], _padcols(wd1[:, H:H + A], KA), wd1[:, H + A:], g(d + "fc_dynamic.3.weight"),
                    g(d + "fc_dynamic.6.weight")]
         r = d + "reward_predictor."
-        chunks.append(_padcols(torch.cat([g(r + "gc1.lin_layer.weight"), g(r + "nn_gc1.weight")], 0), H + KA))
+        wr1 = torch.cat([g(r + "gc1.lin_layer.weight"), g(r + "nn_gc1.weight")], 0)      # (128, 128 + A)
+        chunks += [wr1[:, :H], _padcols(wr1[:, H:H + A], KA)]
         chunks.append(torch.cat([g(r + "gc2.lin_layer.weight"), g(r + "nn_gc2.weight")], 0))
         v = p + "value_predictor."
         chunks.append(torch.cat([g(v + "gc1.lin_layer.weight"), g(v + "nn_gc1.weight")], 0))
@@ -134,7 +135,10 @@ class FusedParams:
                 g(pre + "V.weight"), torch.cat([g(pre + "V.bias"), z16[: 16 - SUP]]))
         bp2 = torch.cat([g(p + "fc_policy.3.bias"), torch.zeros(KA - A, device=dev)])
         put("pol", g(p + "fc_policy.0.bias"), g(p + "fc_policy.1.weight"), g(p + "fc_policy.1.bias"), bp2)
-        vecf = torch.cat(vec).contiguous()
+        vecf = torch.cat(vec)
+        if vecf.numel() % 4:
+            vecf = torch.cat([vecf, torch.zeros(4 - vecf.numel() % 4, device=dev)])
+        vecf = vecf.contiguous()
         assert all(o % 4 == 0 for o in self.off.values())
         if self.wpk is None:
             self.wpk, self.vec = wpk, vecf
@@ -143,7 +147,7 @@ class FusedParams:
             self.vec.copy_(vecf)
 
     def desc(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None, logits_out=None,
-             tree_agents=None, cur=-1, inv_tau=1.0):
+             tree_agents=None, cur=-1, inv_tau=1.0, dbg_clock=None):
         ptr = lambda t: (t.data_ptr() if t is not None else None)
         dsc = InferDesc()
         dsc.B, dsc.N, dsc.A, dsc.KA, dsc.NAP = int(B), self.N, self.A, self.KA, self.KA
@@ -152,7 +156,10 @@ class FusedParams:
         dsc.pool, dsc.idx_x, dsc.actions, dsc.next_hidden = ptr(pool), ptr(idx_x), ptr(actions), ptr(next_hidden)
         dsc.reward, dsc.value, dsc.probs, dsc.beta = ptr(reward), ptr(value), ptr(probs), ptr(beta)
         dsc.greedy, dsc.logits_out = ptr(greedy), ptr(logits_out)
-        dsc.wpk, dsc.vec = self.wpk.data_ptr(), self.vec.data_ptr()
+        dsc.dbg_clock = ptr(dbg_clock)
+        import os as _os
+        dsc.dbg_flags = int(_os.environ.get('MAZ_DBG_FLAGS', '0'))
+        dsc.wpk, dsc.vec, dsc.vec_floats = self.wpk.data_ptr(), self.vec.data_ptr(), self.vec.numel()
         for i in range(NCHUNK):
             dsc.chunk_off[i], dsc.chunk_bytes[i] = self.chunk_off[i], self.chunk_bytes[i]
         o = self.off

@@ -32,3 +32,11 @@ for i in range(n_launch):
 torch.cuda.synchronize()
 print("k_recurrent_inference us per launch:", [round(ev[i].elapsed_time(ev[i + 1]) * 1e3, 1) for i in range(n_launch)])
 print("finite:", bool(torch.isfinite(pool[1]).all()), bool(torch.isfinite(val).all()))
+
+if os.environ.get("STAGE_CLOCKS"):
+    dbg = torch.zeros(256, dtype=torch.int64, device=dev)
+    inf.recurrent_fused(B, pool, idx, act, pool[1], rew, val, probs, beta, dbg_clock=dbg)
+    torch.cuda.synchronize()
+    t = dbg.cpu().numpy()
+    t = t[t > 0]
+    print("stage clocks (cycles since first):", (t - t[0]).tolist())
