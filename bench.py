@@ -354,7 +354,9 @@ def run_ours(args):
                    "mean_search_depth": dbar, "mean_children": cbar, "parallelism": f"roots sharded x{world}"},
         "e2e": {"value": total_sims / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e, "api": "SampledMCTS.batch_search (host numpy + pinned hidden state)"},
-        "gpu_launches": int(args.steps * (3 + (3 if inf.fused is not None else 2) * S)),
+        # our kernels per search: k_seed, k_prepare, k_select (first simulation), per simulation the fused inference
+        # kernel (bf16 mode) and the expand+backup(+next select) kernel, k_readout
+        "gpu_launches": int(args.steps * (4 + (2 if inf.fused is not None else 1) * S)),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_expand_backup", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

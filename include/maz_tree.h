@@ -92,6 +92,13 @@ int maz_tree_batch_expansion_and_backup_dev(maz_tree *t, int hidden_state_index_
                                             int sampled_times, const float *rewards, const float *values,
                                             const float *policy_probs, const float *beta);
 
+/* fused step for the on-device search loop: cbatch_expansion_and_backup of simulation s followed by
+ * cbatch_selection of simulation s+1 in ONE launch (cnode.cpp:644-670 then 616-642). */
+int maz_tree_expansion_backup_selection_dev(maz_tree *t, int hidden_state_index_x, float discount, int sampled_times,
+                                            const float *rewards, const float *values, const float *policy_probs,
+                                            const float *beta, float pb_c_base, float pb_c_init, int *idx_x, int *idx_y,
+                                            int *act);
+
 /* ---- readouts -------------------------------------------------------------------------------------
  * replaces CTree_batch::get_roots_values / get_roots_marginal_visit_count / get_roots_marginal_priors
  * (cnode.cpp:672-700) and get_num_children_of_root (cnode.cpp:702-705). */

@@ -33,6 +33,8 @@ SIGNATURES = {
     "maz_tree_prepare_dev": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_float, _f32p]),
     "maz_tree_batch_selection_dev": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, _i32p, _i32p, _i32p]),
     "maz_tree_batch_expansion_and_backup_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, _f32p, _f32p, _f32p, _f32p]),
+    "maz_tree_expansion_backup_selection_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, _f32p, _f32p, _f32p, _f32p,
+                                                          C.c_float, C.c_float, _i32p, _i32p, _i32p]),
     "maz_tree_get_roots_values": (C.c_int, [C.c_void_p, _f32p]),
     "maz_tree_get_roots_marginal_visit_count": (C.c_int, [C.c_void_p, _i32p]),
     "maz_tree_get_roots_marginal_priors": (C.c_int, [C.c_void_p, _f32p]),

@@ -112,6 +112,7 @@ static int build_layout(TreeLayout &L, int B, int N, int A, int K, int S, float 
     L.off_nchild = take(2ull * Pp);
     L.off_cbase = take(2ull * Pp);
     L.off_hidx = take(2ull * Pp);
+    L.off_eid = take(2ull * Pp);
     L.off_actions = take(1ull * Pp * N);
     L.off_expslot = take(2ull * (S + 4));
     L.off_path = take(2ull * (S + 4));
@@ -187,7 +188,8 @@ int maz_tree_create_ex(maz_tree **out, int B, int N, int A, int K, int S, float 
     if (dyn > 227 * 1024) return fail(MAZ_ERR_UNSUPPORTED, "agent_num*action_space_size too large for the shared-memory staging");
     if (dyn > 48 * 1024) {
         if ((e = cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess ||
-            (e = cudaFuncSetAttribute(k_expand_backup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess)
+            (e = cudaFuncSetAttribute(k_expand_backup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess ||
+            (e = cudaFuncSetAttribute(k_expand_backup_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess)
             return fail(MAZ_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     }
     if ((rc = upload_lam_pow(t)) != MAZ_OK) { std::string m = g_last_error; return fail(rc, m); }
@@ -316,6 +318,25 @@ int maz_tree_batch_expansion_and_backup_dev(maz_tree *t, int hidx, float discoun
     DeviceGuard g(t->device);
     k_expand_backup<<<tree_grid(t), tree_block(t), t->scratch_per_warp * t->wpb, t->stream>>>(
         t->L, t->arena, t->d_lam_pow, hidx, discount, K, rewards, values, probs, beta, t->d_err);
+    CU_TRY(cudaGetLastError());
+    return MAZ_OK;
+}
+
+int maz_tree_expansion_backup_selection_dev(maz_tree *t, int hidx, float discount, int K, const float *rewards,
+                                            const float *values, const float *probs, const float *beta, float c_base,
+                                            float c_init, int *idx_x, int *idx_y, int *act)
+{
+    if (!t) return set_err(MAZ_ERR_INVALID, "null handle");
+    if (!t->prepared) return set_err(MAZ_ERR_INVALID, "expansion before prepare");
+    if (K < 1 || K > t->L.K) return set_err(MAZ_ERR_INVALID, "expansion: sampled_times must be in [1, constructor's sampled_times]");
+    if (hidx < 0 || hidx > 32767) return set_err(MAZ_ERR_INVALID, "expansion: hidden_state_index_x out of range");
+    if (!rewards || !values || !probs || !beta || !idx_x || !idx_y || !act) return set_err(MAZ_ERR_INVALID, "NULL argument");
+    int rc = maz_tree_set_puct(t, c_base, c_init);
+    if (rc) return rc;
+    DeviceGuard g(t->device);
+    k_expand_backup_select<<<tree_grid(t), tree_block(t), t->scratch_per_warp * t->wpb, t->stream>>>(
+        t->L, t->arena, t->d_lam_pow, hidx, discount, K, rewards, values, probs, beta, t->d_logterm, t->d_sqrtn, t->table_len,
+        idx_x, idx_y, act, t->d_err);
     CU_TRY(cudaGetLastError());
     return MAZ_OK;
 }

@@ -34,6 +34,7 @@ MAZ_FIELD(int, f_visit, off_visit)
 MAZ_FIELD(uint16_t, f_nchild, off_nchild)
 MAZ_FIELD(uint16_t, f_cbase, off_cbase)
 MAZ_FIELD(int16_t, f_hidx, off_hidx)
+MAZ_FIELD(uint16_t, f_eid, off_eid)
 MAZ_FIELD(uint8_t, f_actions, off_actions)
 MAZ_FIELD(uint16_t, f_expslot, off_expslot)
 MAZ_FIELD(uint16_t, f_path, off_path)
@@ -160,13 +161,14 @@ struct ExpandScratch {
     double *cp;         // [N*A] cumulative probabilities (std::discrete_distribution::_M_cp)
     long long *keys;    // [32]
     float *beta;        // [N*A]
+    float *probs;       // [N*A] policy probabilities (staged with beta: no dependent global loads later)
     uint32_t *draws;    // [kMtChunk]
     uint8_t *samp;      // [K*N] sampled per-agent actions
 };
 __host__ __device__ inline size_t expand_scratch_bytes(int N, int A, int K)
 {
     size_t na = (size_t)N * A;
-    size_t b = 8 * na + 8 * 32 + 4 * na + 4 * kMtChunk + (size_t)K * N;
+    size_t b = 8 * na + 8 * 32 + 4 * na + 4 * na + 4 * kMtChunk + (size_t)K * N;
     return (b + 15) & ~(size_t)15;
 }
 __device__ __forceinline__ ExpandScratch carve_scratch(char *p, int N, int A)
@@ -176,8 +178,9 @@ __device__ __forceinline__ ExpandScratch carve_scratch(char *p, int N, int A)
     s.cp = reinterpret_cast<double *>(p);
     s.keys = reinterpret_cast<long long *>(p + 8 * na);
     s.beta = reinterpret_cast<float *>(p + 8 * na + 256);
-    s.draws = reinterpret_cast<uint32_t *>(p + 8 * na + 256 + 4 * na);
-    s.samp = reinterpret_cast<uint8_t *>(p + 8 * na + 256 + 4 * na + 4 * kMtChunk);
+    s.probs = reinterpret_cast<float *>(p + 8 * na + 256 + 4 * na);
+    s.draws = reinterpret_cast<uint32_t *>(p + 8 * na + 256 + 8 * na);
+    s.samp = reinterpret_cast<uint8_t *>(p + 8 * na + 256 + 8 * na + 4 * kMtChunk);
     return s;
 }
 
@@ -189,11 +192,14 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
                                            int &err, int slot, int hidx, float reward, float value,
                                            const float *__restrict__ probs, const float *__restrict__ beta,
                                            int K, float eps, const float *__restrict__ noises,
-                                           const ExpandScratch &sc, int lane)
+                                           const ExpandScratch &sc, int lane, bool draws_prefetched = false)
 {
     const int N = L.N, A = L.A, NA = N * A;
 
-    for (int t = lane; t < NA; t += 32) sc.beta[t] = beta[t];
+    for (int t = lane; t < NA; t += 32) {
+        sc.beta[t] = beta[t];
+        sc.probs[t] = probs[t];
+    }
     __syncwarp();
 
     if (A >= 2) {
@@ -216,7 +222,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
         uint32_t *mt = f_mt(L, tb);
         for (int j0 = 0; j0 < KN; j0 += kMtChunk / 2) {
             const int np = min(kMtChunk / 2, KN - j0);
-            mt_fetch(mt, mt_pos, sc.draws, 2 * np, lane);
+            if (!draws_prefetched) mt_fetch(mt, mt_pos, sc.draws, 2 * np, lane);   // else: staged by the caller
             for (int t = lane; t < np; t += 32) {
                 const int j = j0 + t;
                 const int i = j % N;
@@ -280,7 +286,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
         for (int i = 0; i < N; ++i) {
             const int a = sk[i];
             const float pb = sc.beta[i * A + a];
-            const float pp = __ldg(probs + i * A + a);
+            const float pp = sc.probs[i * A + a];
             beta_prob = __fmul_rn(beta_prob, pb);
             pred_prob = __fmul_rn(pred_prob, pp);
             if (eps > 0) {
@@ -311,6 +317,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
         f_wsum(L, tb)[slot] = 0.0f;
         f_wtot(L, tb)[slot] = 0.0f;
         f_expslot(L, tb)[n_expanded] = (uint16_t)slot;
+        f_eid(L, tb)[slot] = (uint16_t)n_expanded;   // expansion order: index of this node's q-delta entry
     }
     tot_nodes = base + C;
     n_expanded += 1;
@@ -319,32 +326,39 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
 }
 
 // ---- SubTreeValueSet::update (utils.cpp:20-71) on the per-tree value log -----------------------------
-// wsum / wtot are the node's weighted_sum / tot_weight (warp-uniform registers, written back by caller).
-__device__ __forceinline__ void vs_update(const TreeLayout &L, char *tb, int &log_len, int &err, float &wsum, float &wtot,
-                                          int slot, int depth, float key, const float *__restrict__ lam_pow, int lane)
+// Scan result for one (node slot, depth) set: sizes and the two order statistics the reference queries.
+struct VsScan {
+    int cnt, nbig;
+    uint32_t minbig, maxsmall;   // order-preserving images (f2ord) of min(big) / max(small), per lane
+    int minpos, maxpos;          // log positions holding them (-1: none in this lane)
+};
+__device__ __forceinline__ void vs_scan_init(VsScan &r)
+{
+    r.cnt = 0; r.nbig = 0; r.minbig = 0xffffffffu; r.maxsmall = 0u; r.minpos = -1; r.maxpos = -1;
+}
+__device__ __forceinline__ void vs_scan_entry(VsScan &r, uint32_t tag, uint32_t k, float v, int e)
+{
+    if ((k & ~1u) == tag) {
+        const uint32_t o = f2ord(v);
+        ++r.cnt;
+        if (k & 1u) {
+            ++r.nbig;
+            if (o < r.minbig || r.minpos < 0) { r.minbig = o; r.minpos = e; }
+        } else {
+            if (o > r.maxsmall || r.maxpos < 0) { r.maxsmall = o; r.maxpos = e; }
+        }
+    }
+}
+// Apply the update given the per-lane scan.  wsum / wtot are the node's weighted_sum / tot_weight
+// (warp-uniform registers, written back by the caller).
+__device__ __forceinline__ void vs_apply(const TreeLayout &L, char *tb, int &log_len, int &err, float &wsum, float &wtot,
+                                         uint32_t tag, int depth, float key, const float *__restrict__ lam_pow, int lane,
+                                         const VsScan &r)
 {
     uint32_t *vk = f_vskey(L, tb);
     float *vv = f_vsval(L, tb);
-    const uint32_t tag = ((uint32_t)slot << 16) | ((uint32_t)depth << 1);
-    int cnt = 0, nbig = 0;
-    uint32_t minbig = 0xffffffffu, maxsmall = 0u;
-    int minpos = -1, maxpos = -1;
-    for (int e = lane; e < log_len; e += 32) {
-        const uint32_t k = vk[e];
-        const float v = vv[e];
-        if ((k & ~1u) == tag) {
-            const uint32_t o = f2ord(v);
-            ++cnt;
-            if (k & 1u) {
-                ++nbig;
-                if (o < minbig || minpos < 0) { minbig = o; minpos = e; }
-            } else {
-                if (o > maxsmall || maxpos < 0) { maxsmall = o; maxpos = e; }
-            }
-        }
-    }
-    cnt = __reduce_add_sync(MAZ_FULL, cnt);
-    nbig = __reduce_add_sync(MAZ_FULL, nbig);
+    const int cnt = __reduce_add_sync(MAZ_FULL, r.cnt);
+    const int nbig = __reduce_add_sync(MAZ_FULL, r.nbig);
     const int nsmall = cnt - nbig;
     const float lp = lam_pow[depth];
     // size_lim = max(1, (int)ceil(count * (1 - quantile)))  (utils.cpp:31; float product, ceil)
@@ -354,13 +368,13 @@ __device__ __forceinline__ void vs_update(const TreeLayout &L, char *tb, int &lo
     bool append_big;
     int flip_pos = -1;       // log entry whose big/small flag flips
     if (nbig == lim) {       // utils.cpp:33-48
-        const uint32_t gmin = __reduce_min_sync(MAZ_FULL, minpos >= 0 ? minbig : 0xffffffffu);
+        const uint32_t gmin = __reduce_min_sync(MAZ_FULL, r.minpos >= 0 ? r.minbig : 0xffffffffu);
         const float m = ord2f(gmin);
         if (key < m) {
             append_big = false;
         } else {
-            const unsigned who = __ballot_sync(MAZ_FULL, minpos >= 0 && minbig == gmin);
-            flip_pos = __shfl_sync(MAZ_FULL, minpos, __ffs(who) - 1);
+            const unsigned who = __ballot_sync(MAZ_FULL, r.minpos >= 0 && r.minbig == gmin);
+            flip_pos = __shfl_sync(MAZ_FULL, r.minpos, __ffs(who) - 1);
             wsum = __fsub_rn(wsum, __fmul_rn(lp, m));
             wtot = __fsub_rn(wtot, lp);
             append_big = true;
@@ -374,15 +388,15 @@ __device__ __forceinline__ void vs_update(const TreeLayout &L, char *tb, int &lo
             wtot = __fadd_rn(wtot, lp);
             wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
         } else {
-            const uint32_t gmax = __reduce_max_sync(MAZ_FULL, maxpos >= 0 ? maxsmall : 0u);
+            const uint32_t gmax = __reduce_max_sync(MAZ_FULL, r.maxpos >= 0 ? r.maxsmall : 0u);
             const float M = ord2f(gmax);
             if (key > M) {
                 append_big = true;
                 wtot = __fadd_rn(wtot, lp);
                 wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
             } else {
-                const unsigned who = __ballot_sync(MAZ_FULL, maxpos >= 0 && maxsmall == gmax);
-                flip_pos = __shfl_sync(MAZ_FULL, maxpos, __ffs(who) - 1);
+                const unsigned who = __ballot_sync(MAZ_FULL, r.maxpos >= 0 && r.maxsmall == gmax);
+                flip_pos = __shfl_sync(MAZ_FULL, r.maxpos, __ffs(who) - 1);
                 wtot = __fadd_rn(wtot, lp);
                 wsum = __fadd_rn(wsum, __fmul_rn(lp, M));
                 append_big = false;
@@ -399,6 +413,20 @@ __device__ __forceinline__ void vs_update(const TreeLayout &L, char *tb, int &lo
         vv[log_len] = key;
     }
     log_len += 1;
+}
+__device__ __forceinline__ uint32_t vs_tag(int slot, int depth) { return ((uint32_t)slot << 16) | ((uint32_t)depth << 1); }
+
+// scan the log in global memory (entries [from, log_len)) and apply
+__device__ __forceinline__ void vs_update(const TreeLayout &L, char *tb, int &log_len, int &err, float &wsum, float &wtot,
+                                          int slot, int depth, float key, const float *__restrict__ lam_pow, int lane)
+{
+    const uint32_t *vk = f_vskey(L, tb);
+    const float *vv = f_vsval(L, tb);
+    const uint32_t tag = vs_tag(slot, depth);
+    VsScan r;
+    vs_scan_init(r);
+    for (int e = lane; e < log_len; e += 32) vs_scan_entry(r, tag, vk[e], vv[e], e);
+    vs_apply(L, tb, log_len, err, wsum, wtot, tag, depth, key, lam_pow, lane, r);
     __syncwarp();
 }
 

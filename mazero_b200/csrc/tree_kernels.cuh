@@ -51,7 +51,7 @@ __global__ void k_prepare(TreeLayout L, char *arena, const float *__restrict__ l
         f_beta(L, tb)[0] = 1.0f;
         f_beta_hat(L, tb)[0] = 1.0f;
         f_visit(L, tb)[0] = 0;
-        f_qdelta(L, tb)[0] = 0.0f;
+        f_qdelta(L, tb)[0] = 0.0f;   // (indexed by hidden-state index; the root's entry is never used)
     }
     const size_t NA = (size_t)L.N * L.A;
     const float value = values[tree];
@@ -79,46 +79,61 @@ __global__ void k_prepare(TreeLayout L, char *arena, const float *__restrict__ l
 
 // ---- CTree_batch::cbatch_selection -> CTree::select_path / select_child / ucb_score --------------------
 // (cnode.cpp:616-642, 381-413, 337-379, 297-335)
-__global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ logterm, const double *__restrict__ sqrtn,
-                         int table_len, float discount, int *__restrict__ idx_x, int *__restrict__ idx_y,
-                         int *__restrict__ act_out, int *g_err)
+// Latency-bound pointer chase: ONE memory round trip per tree level.  While the children of the current
+// node are scored, each child's own header (num_children, child_base, visit, pred_value, hidden index) is
+// already in its lane's registers, so descending is a shuffle.  The next few mt19937 outputs are
+// prefetched at kernel start (one raw draw per select_child call).
+__device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ logterm,
+                                                   const double *__restrict__ sqrtn, int table_len, float discount, int tree,
+                                                   int lane, int *__restrict__ idx_x, int *__restrict__ idx_y,
+                                                   int *__restrict__ act_out, int *g_err)
 {
-    int tree, lane;
-    if (!warp_tree(L, tree, lane)) return;
-    char *tb = arena + (size_t)tree * L.slab_bytes;
-    TreeHdr *h = f_hdr(tb);
-    int mt_pos = h->mt_pos;
-    const float mn = h->mm_min, mx = h->mm_max;
-    const int mmc = h->mm_cnt;
     uint16_t *path = f_path(L, tb);
     const uint16_t *nchild = f_nchild(L, tb);
     const uint16_t *cbase = f_cbase(L, tb);
     const int *visit = f_visit(L, tb);
     const float *pred_value = f_pred_value(L, tb);
+    const int16_t *hidx = f_hidx(L, tb);
     uint32_t *mt = f_mt(L, tb);
 
-    int node = 0, parent = 0, len = 0, err = 0;
+    // round trip 0: tree header, root header, prefetched random words
+    int mt_pos = h->mt_pos;
+    const float mn = h->mm_min, mx = h->mm_max;
+    const int mmc = h->mm_cnt;
+    int C = nchild[0], base = cbase[0], vc = visit[0];
+    float pq = pred_value[0];
+    constexpr int kPre = 8;
+    uint32_t pre = 0;                          // lane l < kPre holds raw state word mt_pos + l (if in this block)
+    if (lane < kPre && mt_pos + lane < kMtN) pre = mt[mt_pos + lane];
+    int pre_used = 0;                          // draws consumed from the prefetched words
+    const int pre_avail = min(kPre, max(0, kMtN - mt_pos));
+
+    int node = 0, parent_hidx = 0, node_hidx = 0, len = 0, err = 0;
     if (lane == 0) path[0] = 0;
-    while (true) {
-        const int C = nchild[node];
-        if (C == 0) break;
-        const int base = cbase[node];
-        const int vc = visit[node];
+    while (C > 0) {
+        // round trip `len+1`: children fields + the children's own headers
+        float prior = 0.f, rew = 0.f, ws = 0.f, wt = 1.f, cpq = 0.f;
+        int cvis = 0, cC = 0, cbase_c = 0, chidx = -1;
+        if (lane < C) {
+            const int cs = base + lane;
+            prior = f_prior(L, tb)[cs];
+            cvis = visit[cs];
+            rew = f_reward(L, tb)[cs];
+            cC = nchild[cs];
+            cbase_c = cbase[cs];
+            cpq = pred_value[cs];
+            chidx = hidx[cs];
+            ws = f_wsum(L, tb)[cs];   // unconditional (garbage for never-visited children, unused then):
+            wt = f_wtot(L, tb)[cs];   // keeps every load of this level in ONE round trip
+        }
         int ci;
         if (node == 0 && vc <= C) {
             ci = vc - 1;  // forced root round-robin, no RNG draw (cnode.cpp:398-399)
         } else {
-            const float pq = pred_value[node];
             int n = vc - 1;
             if (n >= table_len) n = table_len - 1;
             float score = 0.0f;
             if (lane < C) {
-                const int cs = base + lane;
-                const float prior = f_prior(L, tb)[cs];
-                const int cvis = visit[cs];
-                const float rew = f_reward(L, tb)[cs];
-                const float ws = f_wsum(L, tb)[cs];
-                const float wt = f_wtot(L, tb)[cs];
                 // pb_c = log((n + c_base + 1)/c_base) + c_init   [float <- double]   (host table)
                 // pb_c *= sqrt(n) / (visit + 1)                   [float <- double product]
                 const float pb_c = (float)__dmul_rn((double)logterm[n], __ddiv_rn(sqrtn[n], (double)(cvis + 1)));
@@ -154,12 +169,25 @@ __global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ lo
             const int nl = __popc(listmask);
             ci = 0;
             if (nl > 0) {  // one raw draw even for a single candidate (cnode.cpp:373-377)
-                const uint32_t r = mt_next(mt, mt_pos, lane);
+                uint32_t r;
+                if (pre_used < pre_avail) {
+                    r = mt_temper(__shfl_sync(MAZ_FULL, pre, pre_used));
+                    ++pre_used;
+                    ++mt_pos;
+                } else {
+                    r = mt_next(mt, mt_pos, lane);
+                }
                 ci = (int)__fns(listmask, 0, (int)(r % (uint32_t)nl) + 1);
             }
         }
-        parent = node;
+        // descend: the chosen child's header is in lane ci's registers
+        parent_hidx = node_hidx;
         node = base + ci;
+        node_hidx = __shfl_sync(MAZ_FULL, chidx, ci);
+        C = __shfl_sync(MAZ_FULL, cC, ci);
+        base = __shfl_sync(MAZ_FULL, cbase_c, ci);
+        vc = __shfl_sync(MAZ_FULL, cvis, ci);
+        pq = __shfl_sync(MAZ_FULL, cpq, ci);
         ++len;
         if (len > L.S + 1) {
             err = kErrPathOverflow;
@@ -171,7 +199,7 @@ __global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ lo
         h->path_len = len;
         h->mt_pos = mt_pos;
         h->sum_path_len += len;
-        idx_x[tree] = f_hidx(L, tb)[parent];
+        idx_x[tree] = parent_hidx;
         idx_y[tree] = tree;
         if (err) {
             h->err = err;
@@ -182,56 +210,121 @@ __global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ lo
     for (int j = lane; j < L.N; j += 32) act_out[(size_t)tree * L.N + j] = act[j];
 }
 
-// ---- CTree_batch::cbatch_expansion_and_backup -> expand_and_backprop / back_propagate ------------------
-// (cnode.cpp:644-670, 452-469, 415-450)
-__global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restrict__ lam_pow, int hidx, float discount,
-                                int K, const float *__restrict__ rewards, const float *__restrict__ values,
-                                const float *__restrict__ probs, const float *__restrict__ beta, int *g_err)
+__global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ logterm, const double *__restrict__ sqrtn,
+                         int table_len, float discount, int *__restrict__ idx_x, int *__restrict__ idx_y,
+                         int *__restrict__ act_out, int *g_err)
 {
-    extern __shared__ __align__(16) char smem[];
     int tree, lane;
     if (!warp_tree(L, tree, lane)) return;
     char *tb = arena + (size_t)tree * L.slab_bytes;
-    TreeHdr *h = f_hdr(tb);
-    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+    select_path_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
+}
 
+// ---- CTree_batch::cbatch_expansion_and_backup -> expand_and_backprop / back_propagate ------------------
+// (cnode.cpp:644-670, 452-469, 415-450)
+// Latency plan: everything the backup needs is requested up front, in parallel with the expansion:
+//   round trip 1: tree header;   round trip 2: path[], the value log (first 256 entries, in registers),
+//   the mt19937 words of this expansion, beta / probs;   round trip 3: per-path-node fields (lane i <-> path[i]).
+// The log snapshot stays valid for the whole backup: every path node owns a distinct (slot, depth) tag, and
+// entries appended / flags flipped for one node never match another node's tag.
+constexpr int kLogRegs = 8;   // 8 x 32 log entries cached in registers; longer logs: tail scanned from memory
+
+__device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ lam_pow,
+                                                     int hidx, float discount, int K, float reward_in, float value,
+                                                     const float *__restrict__ probs, const float *__restrict__ beta,
+                                                     const ExpandScratch &sc, int lane, int *g_err)
+{
     int tot_nodes = h->tot_nodes, log_len = h->log_len, mt_pos = h->mt_pos, n_expanded = h->n_expanded, err = h->err;
     const int len = h->path_len;
+    const int log_len0 = log_len;
+    const int leaf_eid = n_expanded;                  // expansion order the leaf is about to get
     const uint16_t *path = f_path(L, tb);
-    const int leaf = path[len];
-    const size_t NA = (size_t)L.N * L.A;
-    const float value = values[tree];
-
-    expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, rewards[tree], value, probs + tree * NA,
-                beta + tree * NA, K, 0.0f, nullptr, sc, lane);
-
+    const uint32_t *vk = f_vskey(L, tb);
+    const float *vv = f_vsval(L, tb);
     float *reward = f_reward(L, tb), *wsum = f_wsum(L, tb), *wtot = f_wtot(L, tb);
+
+    // ---- round trip 2: issue everything that depends only on the header -------------------------------------
+    const bool fast = len < 32;                       // path fits one lane per node (else: per-node loads below)
+    int my_slot = 0;
+    if (fast && lane <= len) my_slot = path[lane];
+    uint32_t lk[kLogRegs];
+    float lv[kLogRegs];
+#pragma unroll
+    for (int c = 0; c < kLogRegs; ++c) {
+        const int e = c * 32 + lane;
+        lk[c] = (e < log_len0) ? vk[e] : 0xffffffffu;   // tag 0x7fffffff<<1 never matches (slot < 65536, depth < 32768)
+        lv[c] = (e < log_len0) ? vv[e] : 0.0f;
+    }
+    const int n_draw = (L.A >= 2) ? 2 * K * L.N : 0;
+    const bool draws_pre = n_draw > 0 && n_draw <= kMtChunk && mt_pos + n_draw <= kMtN;
+    if (draws_pre) {
+        const uint32_t *mt = f_mt(L, tb);
+        for (int t = lane; t < n_draw; t += 32) sc.draws[t] = mt_temper(mt[mt_pos + t]);
+        mt_pos += n_draw;
+    }
+    // ---- round trip 3: per-path-node fields, lane i <-> path[i] ------------------------------------------------
+    const int leaf = fast ? __shfl_sync(MAZ_FULL, my_slot, len) : (int)path[len];
+    float my_rew = 0.f, my_ws = 0.f, my_wt = 0.f, my_ppv = 0.f;
+    int my_vis = 0, my_hidx = 0;
+    if (fast && lane < len) {                         // the leaf (lane == len) is filled by the expansion below
+        my_rew = reward[my_slot];
+        my_ws = wsum[my_slot];
+        my_wt = wtot[my_slot];
+        my_vis = f_visit(L, tb)[my_slot];
+        my_hidx = f_eid(L, tb)[my_slot];
+    }
+    {
+        const int prev = __shfl_up_sync(MAZ_FULL, my_slot, 1);
+        if (fast && lane >= 1 && lane <= len) my_ppv = f_pred_value(L, tb)[prev];   // parent's pred_value
+    }
+
+    expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, reward_in, value, probs, beta, K, 0.0f, nullptr, sc,
+                lane, draws_pre);
+
+    // ---- back_propagate (cnode.cpp:415-450) -----------------------------------------------------------------------
+    float *qd = f_qdelta(L, tb);                      // q-delta of the e-th expanded node (the CMinMaxStats entries)
     float G = value;
     for (int i = len; i >= 0; --i) {
-        const int slot = path[i];
-        const float rew = reward[slot];
-        float ws = wsum[slot], wt = wtot[slot];
-        // (the reference removes the node's old q-delta from the min-max multiset here; in this layout
-        //  the entry simply lives in qdelta[slot] and is overwritten below)
-        vs_update(L, tb, log_len, err, ws, wt, slot, len - i, G, lam_pow, lane);
+        int slot, vis, nh;
+        float rew, ws, wt, ppv;
+        if (fast) {
+            slot = __shfl_sync(MAZ_FULL, my_slot, i);
+            rew = __shfl_sync(MAZ_FULL, my_rew, i);
+            ws = __shfl_sync(MAZ_FULL, my_ws, i);
+            wt = __shfl_sync(MAZ_FULL, my_wt, i);
+            vis = __shfl_sync(MAZ_FULL, my_vis, i);
+            nh = __shfl_sync(MAZ_FULL, my_hidx, i);
+            ppv = __shfl_sync(MAZ_FULL, my_ppv, i);
+        } else {
+            slot = path[i];
+            rew = reward[slot]; ws = wsum[slot]; wt = wtot[slot];
+            vis = f_visit(L, tb)[slot];
+            nh = f_eid(L, tb)[slot];
+            ppv = (i > 0) ? f_pred_value(L, tb)[path[i - 1]] : 0.f;
+        }
+        if (i == len) { rew = reward_in; ws = 0.f; wt = 0.f; vis = 0; nh = leaf_eid; }   // freshly expanded leaf
+        // (the reference removes the node's old q-delta from the min-max multiset here; in this layout the
+        //  entry simply lives in qd[hidden index] and is overwritten below)
+        const uint32_t tag = vs_tag(slot, len - i);
+        VsScan r;
+        vs_scan_init(r);
+#pragma unroll
+        for (int c = 0; c < kLogRegs; ++c) vs_scan_entry(r, tag, lk[c], lv[c], c * 32 + lane);
+        for (int e = kLogRegs * 32 + lane; e < log_len0; e += 32) vs_scan_entry(r, tag, vk[e], vv[e], e);
+        vs_apply(L, tb, log_len, err, ws, wt, tag, len - i, G, lam_pow, lane, r);
         if (lane == 0) {
-            f_visit(L, tb)[slot] += 1;
+            f_visit(L, tb)[slot] = vis + 1;
             wsum[slot] = ws;
             wtot[slot] = wt;
-            if (i != 0) {
-                const float pv = f_pred_value(L, tb)[path[i - 1]];
-                f_qdelta(L, tb)[slot] = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), pv);
-            }
+            if (i != 0) qd[nh] = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), ppv);
         }
         G = __fadd_rn(rew, __fmul_rn(discount, G));
     }
     __syncwarp();
     // CMinMaxStats min / max = reduction over the q-deltas of all visited (= expanded) non-root nodes
     uint32_t lo = 0xffffffffu, hi = 0u;
-    const uint16_t *expslot = f_expslot(L, tb);
-    const float *qdelta = f_qdelta(L, tb);
     for (int e = 1 + lane; e < n_expanded; e += 32) {
-        const uint32_t o = f2ord(qdelta[expslot[e]]);
+        const uint32_t o = f2ord(qd[e]);
         lo = min(lo, o);
         hi = max(hi, o);
     }
@@ -248,6 +341,40 @@ __global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restri
         h->err = err;
         if (err) *g_err = err;
     }
+}
+
+__global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restrict__ lam_pow, int hidx, float discount,
+                                int K, const float *__restrict__ rewards, const float *__restrict__ values,
+                                const float *__restrict__ probs, const float *__restrict__ beta, int *g_err)
+{
+    extern __shared__ __align__(16) char smem[];
+    int tree, lane;
+    if (!warp_tree(L, tree, lane)) return;
+    char *tb = arena + (size_t)tree * L.slab_bytes;
+    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+    const size_t NA = (size_t)L.N * L.A;
+    expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards[tree], values[tree], probs + tree * NA,
+                         beta + tree * NA, sc, lane, g_err);
+}
+
+// ---- fused: expansion + backup of simulation s, then selection of simulation s+1 (one launch per simulation
+// in the on-device search loop: the tree's header and hot nodes are still in L1) ------------------------------------
+__global__ void k_expand_backup_select(TreeLayout L, char *arena, const float *__restrict__ lam_pow, int hidx, float discount,
+                                       int K, const float *__restrict__ rewards, const float *__restrict__ values,
+                                       const float *__restrict__ probs, const float *__restrict__ beta,
+                                       const float *__restrict__ logterm, const double *__restrict__ sqrtn, int table_len,
+                                       int *__restrict__ idx_x, int *__restrict__ idx_y, int *__restrict__ act_out, int *g_err)
+{
+    extern __shared__ __align__(16) char smem[];
+    int tree, lane;
+    if (!warp_tree(L, tree, lane)) return;
+    char *tb = arena + (size_t)tree * L.slab_bytes;
+    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+    const size_t NA = (size_t)L.N * L.A;
+    expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards[tree], values[tree], probs + tree * NA,
+                         beta + tree * NA, sc, lane, g_err);
+    __syncwarp();
+    select_path_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
 }
 
 // ---- readouts (cnode.cpp:69-171, 471-530, 672-781) ------------------------------------------------------

@@ -13,8 +13,8 @@
 // operation order.
 //
 // The reference's CMinMaxStats multiset (utils.h:42-53) holds exactly one entry per visited non-root
-// node (cnode.cpp:431-446): here it is the per-slot array `qdelta`, reduced over the tree's list of
-// expanded slots at the end of each backup; selection reads the cached (min,max).
+// node (cnode.cpp:431-446): here it is the array `qdelta`, indexed by the node's expansion order (`eid`, the
+// e-th expanded node of the tree), reduced at the end of each backup; selection reads the cached (min,max).
 #pragma once
 #include <stdint.h>
 
@@ -46,7 +46,7 @@ struct TreeLayout {
     unsigned long long slab_bytes;
     // byte offsets inside a slab (all multiples of 128)
     unsigned off_mt, off_prior, off_pred_prob, off_beta, off_beta_hat, off_reward, off_pred_value, off_wsum, off_wtot,
-        off_qdelta, off_visit, off_nchild, off_cbase, off_hidx, off_actions, off_expslot, off_path, off_vskey, off_vsval;
+        off_qdelta, off_visit, off_nchild, off_cbase, off_hidx, off_eid, off_actions, off_expslot, off_path, off_vskey, off_vsval;
 };
 
 // device error codes stored in TreeHdr::err / the handle's global error word

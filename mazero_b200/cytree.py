@@ -155,6 +155,18 @@ class Tree_batch:
                                                       int(sampled_times), r.ctypes.data, v.ctypes.data, p.ctypes.data,
                                                       b.ctypes.data))
 
+    def expansion_backup_selection_device(self, hidden_state_index_x, discount, sampled_times, rewards, values, policy_probs,
+                                          beta, pb_c_base, pb_c_init, idx_x, idx_y, actions):
+        """Fused step of the on-device loop: batch_expansion_and_backup(s) then batch_selection(s+1), one launch."""
+        self._cache.clear()
+        B, N, NA = self.root_num, self.agent_num, self.agent_num * self.action_space_size
+        check(lib.maz_tree_expansion_backup_selection_dev(
+            self._h, int(hidden_state_index_x), float(discount), int(sampled_times),
+            _dev_ptr(rewards, "float32", B, "rewards"), _dev_ptr(values, "float32", B, "values"),
+            _dev_ptr(policy_probs, "float32", B * NA, "policy_probs"), _dev_ptr(beta, "float32", B * NA, "beta"),
+            float(pb_c_base), float(pb_c_init), _dev_ptr(idx_x, "int32", B, "idx_x"), _dev_ptr(idx_y, "int32", B, "idx_y"),
+            _dev_ptr(actions, "int32", B * N, "actions")))
+
     # ---- readouts (cytree.pyx:93-241) ------------------------------------------------------------------
     def readout(self, discount=0.0):
         """Everything observable at the roots as padded arrays (one kernel, one round of copies)."""

@@ -126,9 +126,13 @@ class _DevicePlan:
             self.out_np[name] = host_np[o:o + n].view(np.float32 if dt is f32 else np.int32).reshape(shp)
             o += n
 
-    def _simulate(self, s):
+    def _simulate(self, s, select_first=True, select_next=False):
+        """One simulation.  select_first: run the selection kernel at the start (else the previous simulation's
+        fused expand+backup+select launch already did); select_next: fuse the NEXT simulation's selection into
+        this simulation's expansion+backup launch."""
         t, B = self.tree, self.B
-        t.batch_selection_device(self.c_base, self.c_init, self.discount, self.idx_x, self.idx_y, self.act)
+        if select_first:
+            t.batch_selection_device(self.c_base, self.c_init, self.discount, self.idx_x, self.idx_y, self.act)
         flat = None
         if self.cur is None:
             joint = self.act
@@ -145,7 +149,11 @@ class _DevicePlan:
             if self.record is not None:
                 self.record.append((self.sim_r.clone(), self.sim_v.clone(), self.sim_p.clone(), self.sim_b.clone(),
                                     self.idx_x.clone(), self.act.clone()))
-            t.batch_expansion_and_backup(s + 1, self.discount, self.K, self.sim_r, self.sim_v, self.sim_p, self.sim_b)
+            if select_next:
+                t.expansion_backup_selection_device(s + 1, self.discount, self.K, self.sim_r, self.sim_v, self.sim_p,
+                                                    self.sim_b, self.c_base, self.c_init, self.idx_x, self.idx_y, self.act)
+            else:
+                t.batch_expansion_and_backup(s + 1, self.discount, self.K, self.sim_r, self.sim_v, self.sim_p, self.sim_b)
             return
         if flat is None:
             flat = self.idx_x.long() * B + self.rows
@@ -160,11 +168,17 @@ class _DevicePlan:
         p, b = p.contiguous(), b.contiguous()
         if self.record is not None:
             self.record.append((rew.clone(), val.clone(), p.clone(), b.clone(), self.idx_x.clone(), self.act.clone()))
-        t.batch_expansion_and_backup(s + 1, self.discount, self.K, rew, val, p, b)
+        if select_next:
+            t.expansion_backup_selection_device(s + 1, self.discount, self.K, rew, val, p, b, self.c_base, self.c_init,
+                                                self.idx_x, self.idx_y, self.act)
+        else:
+            t.batch_expansion_and_backup(s + 1, self.discount, self.K, rew, val, p, b)
 
     def _loop(self):
+        # two launches per simulation: [inference] -> [expand + backup + next selection]
+        fuse = self.record is None
         for s in range(self.S):
-            self._simulate(s)
+            self._simulate(s, select_first=(s == 0 or not fuse), select_next=(fuse and s + 1 < self.S))
 
     def run(self, seed, cfg, noise_eps, root_hidden, rewards, values, probs, beta, noises, root_greedy, factor,
             root_index_offset=0):
