@@ -12,7 +12,8 @@ joint actions, synthetic root hidden states and random-init weights of the refer
 `e2e`     the same metric through the public API a worker calls (`SampledMCTS.batch_search`) with HOST
           buffers: numpy root preparation, H2D of the root tensors from pinned memory, the search, D2H of
           all readouts.
-`roofline`     the dominant tree kernel (expand+backup) against the measured HBM copy peak.
+`roofline`     the dominant kernel of the step (fused inference, ~75 % of GPU time) against the measured sustained
+               bf16 peak; `roofline_tree`: the tree kernel (expand+backup+select) against the measured HBM copy peak.
 `cpu_baseline` the reference CPU path (reference C++ tree compiled into oracle/_ref when available, the
           reference's Python loop restated, the same weights on torch-CPU) on the box's host cores.
 `--impl reference` times that CPU path alone (the reference arm).
@@ -289,18 +290,17 @@ def run_ours(args):
     cbar = float((tot_nodes.sum() - B)) / float(sum_exp)
     plan.tree.reset(7, cfg.tree_value_stat_delta_lb, cfg.mcts_rho, cfg.mcts_lambda, root_off)
     plan.tree.prepare(plan.root_r, plan.root_v, plan.root_p, plan.root_b, K, cfg.root_exploration_fraction, plan.root_n)
-    sel_ev, exp_ev, inf_ev = [], [], []
-    # keep the GPU busy while the host enqueues the whole eager loop, so that the event pairs bracket
-    # back-to-back GPU execution and not host launch latency
+    # the loop the CUDA graph runs: [k_recurrent_inference] -> [k_expand_backup_select]; timed eagerly behind a GPU sleep
+    # so that the event pairs bracket back-to-back GPU execution and not host launch latency
+    tree_ev, inf_ev = [], []
     torch.cuda._sleep(int(2.0e8))
+    plan.tree.batch_selection_device(cfg.pb_c_base, cfg.pb_c_init, cfg.discount, plan.idx_x, plan.idx_y, plan.act)
     for s in range(S):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        e[0].record(stream)
-        plan.tree.batch_selection_device(cfg.pb_c_base, cfg.pb_c_init, cfg.discount, plan.idx_x, plan.idx_y, plan.act)
-        e[1].record(stream)
-        flat = plan.idx_x.long() * B + plan.rows
-        joint = plan.act if cur is None else torch.cat(
-            [plan.factor[:, :cur], plan.act, plan.greedy.view(-1, N).index_select(0, flat)[:, cur + 1:]], dim=1).contiguous()
+        joint = plan.act
+        if cur is not None:
+            flat = plan.idx_x.long() * B + plan.rows
+            joint = torch.cat([plan.factor[:, :cur], plan.act, plan.greedy.view(-1, N).index_select(0, flat)[:, cur + 1:]],
+                              dim=1).contiguous()
         if inf.fused is not None:
             ei = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             ei[0].record(stream)
@@ -310,6 +310,7 @@ def run_ours(args):
             inf_ev.append(ei)
             rew, val, p, bta = plan.sim_r, plan.sim_v, plan.sim_p, plan.sim_b
         else:
+            flat = plan.idx_x.long() * B + plan.rows
             h = plan.pool.view(-1, N * inf.H).index_select(0, flat)
             _, rew, val, logits = inf.recurrent(h, joint, out_hidden=plan.pool[s + 1])
             if cur is not None:
@@ -317,26 +318,38 @@ def run_ours(args):
             p = torch.softmax(logits, dim=-1)
             bta = (p / p.sum(dim=-1, keepdim=True)).contiguous()
             p = p.contiguous()
-        e[2].record(stream)
-        plan.tree.batch_expansion_and_backup(s + 1, cfg.discount, K, rew, val, p, bta)
-        e[3].record(stream)
-        sel_ev.append((e[0], e[1]))
-        exp_ev.append((e[2], e[3]))
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e[0].record(stream)
+        plan.tree.expansion_backup_selection_device(s + 1, cfg.discount, K, rew, val, p, bta, cfg.pb_c_base, cfg.pb_c_init,
+                                                    plan.idx_x, plan.idx_y, plan.act)
+        e[1].record(stream)
+        tree_ev.append(e)
     torch.cuda.synchronize(dev)
-    ms_sel = float(np.mean([a.elapsed_time(b) for a, b in sel_ev]))
-    ms_exp = float(np.mean([a.elapsed_time(b) for a, b in exp_ev]))
+    ms_tree = float(np.mean([a.elapsed_time(b) for a, b in tree_ev]))
     ms_inf = float(np.mean([a.elapsed_time(b) for a, b in inf_ev])) if inf_ev else None
-    # algorithmic bytes per root-simulation of the expand+backup kernel:
-    #   8 + 8*N*A   reward, value, probs, beta in      16 + C*(4N + 36)  leaf header + per-child fields
-    #   40*(d+1)    backup: visit, wsum/wtot r/w, value-log append, min-max entry r/w
-    bytes_exp = B * (8 + 8 * Nt * A + 16 + cbar * (4 * Nt + 36) + 40 * (dbar + 1))
-    bytes_sel = B * (dbar * (16 + 20 * cbar) + 4 * (2 + Nt))
-    peak, peak_src = peaks()
-    achieved = bytes_exp / (ms_exp * 1e-3) / 1e9
-    traffic = None
+    # algorithmic bytes per root-simulation of the tree step:
+    #   expansion + backup: 8 + 8*N*A  reward, value, probs, beta in;  16 + C*(4N + 36)  leaf header + per-child fields;
+    #                       40*(d+1)   visit, wsum/wtot r/w, value-log append, min-max entry r/w
+    #   selection:          d*(16 + 20*C) parent header + per-child prior, visit, reward, wsum, wtot;  4*(2+N) idx, idy, act
+    bytes_tree = B * (8 + 8 * Nt * A + 16 + cbar * (4 * Nt + 36) + 40 * (dbar + 1) + dbar * (16 + 20 * cbar) + 4 * (2 + Nt))
+    hbm_peak, peak_src = peaks()
+    traffic = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(f"k_expand_backup:{args.workload}:{args.mode}")
+    if os.path.exists(tp) and args.workload == "3m" and args.mode == "joint":
+        traffic = json.load(open(tp))
+    tree_roof = {"bound": "hbm", "kernel": "k_expand_backup_select", "achieved": bytes_tree / (ms_tree * 1e-3) / 1e9,
+                 "peak": hbm_peak, "unit": "GB/s", "frac": bytes_tree / (ms_tree * 1e-3) / 1e9 / hbm_peak,
+                 "traffic": (traffic.get("k_expand_backup:3m:joint", 0) + traffic.get("k_select:3m:joint", 0)) or None,
+                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_tree, "launch_ms": ms_tree}
+    if ms_inf is not None:   # the dominant kernel of the step (~75 % of the GPU time): tensor-pipe roofline
+        flop = B * FLOP_PER_ROOT.get(args.workload, 0.0)
+        roofline = {"bound": "tensor", "kernel": "k_recurrent_inference", "achieved": flop / (ms_inf * 1e-3) / 1e12,
+                    "peak": bf16_peak(), "unit": "TFLOP/s", "frac": flop / (ms_inf * 1e-3) / 1e12 / bf16_peak(),
+                    "traffic": traffic.get("k_recurrent_inference:3m:joint"), "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)",
+                    "algorithmic_flop_per_launch": flop, "launch_ms": ms_inf,
+                    "note": "latency-bound 25-stage chain per 128-row tile; see DESIGN.md section 5"}
+    else:
+        roofline = tree_roof
 
     if rank != 0:
         if world > 1:
@@ -358,15 +371,8 @@ def run_ours(args):
         # kernel (bf16 mode) and the expand+backup(+next select) kernel, k_readout
         "gpu_launches": int(args.steps * (4 + (2 if inf.fused is not None else 1) * S)),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_expand_backup", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": bytes_exp, "launch_ms": ms_exp,
-                     "k_select": {"algorithmic_bytes_per_launch": bytes_sel, "launch_ms": ms_sel,
-                                  "achieved": bytes_sel / (ms_sel * 1e-3) / 1e9},
-                     "k_recurrent_inference": None if ms_inf is None else {
-                         "bound": "tensor", "launch_ms": ms_inf, "flop_per_launch": B * FLOP_PER_ROOT.get(args.workload, 0.0),
-                         "achieved_tflops": B * FLOP_PER_ROOT.get(args.workload, 0.0) / (ms_inf * 1e-3) / 1e12,
-                         "peak_tflops": bf16_peak()}},
+        "roofline": roofline,
+        "roofline_tree": tree_roof,
     }
     if not args.no_cpu_baseline and world == 1:
         # bounded sample of the same workload on the host cores (one warm-up + two timed searches)
