@@ -33,6 +33,7 @@ constexpr int SUP = 11;       // DiscreteSupport(-5, 5)
 constexpr int NLAYER = 3;     // AttentionEncoder(3, ...)    (model.py:221)
 constexpr int NCHUNK = MAZ_INFER_NCHUNK;
 constexpr int NSLOT = 3;
+constexpr int NEPI_THREADS = 512;   // epilogue threads (16 warps)
 constexpr uint32_t SLOT_BYTES = 128 * 128 * 2;
 
 enum : uint32_t { TM_X = 0, TM_Q = 128, TM_K = 256, TM_V = 384, TM_ACC = 128 };
@@ -72,10 +73,11 @@ __device__ __noinline__ void mma_chunk(Pipe &p, uint32_t dst, uint32_t a_addr, u
     mma_commit(&p.empty[s]);     // slot reusable once these MMAs have completed
     p.c = c + 1;
 }
-__device__ __noinline__ void mma_stage_begin(Pipe &p)   // all epilogue threads have published their operands
+// "operands ready" hand-off: the 512 epilogue threads and the 32 lanes of the MMA warp meet on hardware named
+// barrier 5 (bar.sync, tens of cycles) -- one mbarrier hop less per stage than arrive + try_wait polling.
+__device__ __forceinline__ void mma_stage_begin()
 {
-    mbar_wait(p.ready, p.ready_phase);
-    p.ready_phase ^= 1;
+    named_bar_sync(5, NEPI_THREADS + 32);
     tc_fence_after();
 }
 __device__ __forceinline__ void mma_stage_end(Pipe &p) { mma_commit(p.mma); }
@@ -169,6 +171,7 @@ __device__ __forceinline__ float support_to_scalar(const float (&lg)[SUP])
 // across the PARTS threads of a row through shared memory + a 128-thread named barrier per quadrant.
 constexpr int PARTS = 4;
 constexpr int NEPI = 128 * PARTS;          // epilogue threads
+static_assert(NEPI == NEPI_THREADS, "epilogue thread count");
 constexpr int NTHREADS = NEPI + 64;        // + producer warp + MMA warp
 constexpr int CP = H / PARTS;        // 32
 constexpr int GP = GH / PARTS;       // 16
@@ -559,60 +562,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
         }
     } else if (warp == NEPI / 32 + 1) {
         // ================================ MMA issuer ==========================================================
-        if ((tid & 31) == 0) {
+        {
+            const bool issuer = (tid & 31) == 0;   // all 32 lanes take part in the named barrier, lane 0 issues
             Pipe p{bar_full, bar_empty, &bar_mma, &bar_ready, smem_u32(sW), tmem, 0, 0, (d.dbg_flags & 2)};
             const uint32_t uKA = (uint32_t)KA;
-            mma_stage_begin(p);                                   // in-proj: W_in [h | onehot]
-            mma_chunk(p, TM_ACC, aT, H, 128, 0);
-            mma_chunk(p, TM_ACC, aOne, uKA, 128, 1);
-            mma_stage_end(p);
+            mma_stage_begin();                                   // in-proj: W_in [h | onehot]
+            if (issuer) mma_chunk(p, TM_ACC, aT, H, 128, 0);
+            if (issuer) mma_chunk(p, TM_ACC, aOne, uKA, 128, 1);
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
 #pragma unroll 1
             for (int l = 0; l < NLAYER; ++l) {
-                mma_stage_begin(p);                               // q, k, v projections
-                mma_chunk(p, TM_Q, aX, H, 128, 0);
-                mma_chunk(p, TM_K, aX, H, 128, 0);
-                mma_chunk(p, TM_V, aX, H, 128, 0);
-                mma_stage_end(p);
-                mma_stage_begin(p);                               // x += sa Wo^T (residual = accumulate into X)
-                mma_chunk(p, TM_X, aT, H, 128, 1);
-                mma_stage_end(p);
-                mma_stage_begin(p);                               // linear1
-                mma_chunk(p, TM_ACC, aX, H, 128, 0);
-                mma_stage_end(p);
-                mma_stage_begin(p);                               // x += f W2^T
-                mma_chunk(p, TM_X, aT, H, 128, 1);
-                mma_stage_end(p);
+                mma_stage_begin();                               // q, k, v projections
+                if (issuer) mma_chunk(p, TM_Q, aX, H, 128, 0);
+                if (issuer) mma_chunk(p, TM_K, aX, H, 128, 0);
+                if (issuer) mma_chunk(p, TM_V, aX, H, 128, 0);
+                if (issuer) mma_stage_end(p);
+                __syncwarp();
+                mma_stage_begin();                               // x += sa Wo^T (residual = accumulate into X)
+                if (issuer) mma_chunk(p, TM_X, aT, H, 128, 1);
+                if (issuer) mma_stage_end(p);
+                __syncwarp();
+                mma_stage_begin();                               // linear1
+                if (issuer) mma_chunk(p, TM_ACC, aX, H, 128, 0);
+                if (issuer) mma_stage_end(p);
+                __syncwarp();
+                mma_stage_begin();                               // x += f W2^T
+                if (issuer) mma_chunk(p, TM_X, aT, H, 128, 1);
+                if (issuer) mma_stage_end(p);
+                __syncwarp();
             }
-            mma_stage_begin(p);                                   // fc_dynamic.0 on [h | onehot | attn]
-            mma_chunk(p, TM_ACC, aT, H, 128, 0);
-            mma_chunk(p, TM_ACC, aOne, uKA, 128, 1);
-            mma_chunk(p, TM_ACC, aX, H, 128, 1);
-            mma_stage_end(p);
-            mma_stage_begin(p);
-            mma_chunk(p, TM_ACC, aT, H, 128, 0);                  // fc_dynamic.3
-            mma_stage_end(p);
-            mma_stage_begin(p);
-            mma_chunk(p, TM_ACC, aX, H, 128, 0);                  // fc_dynamic.6
-            mma_stage_end(p);
-            mma_stage_begin(p);                                   // reward GNN layer 1 on [h' | onehot]
-            mma_chunk(p, TM_ACC, aT, H, 128, 0);
-            mma_chunk(p, TM_ACC, aOne, uKA, 128, 1);
-            mma_stage_end(p);
-            mma_stage_begin(p);
-            mma_chunk(p, TM_ACC, aX, GH, 128, 0);                 // reward GNN layer 2
-            mma_stage_end(p);
-            mma_stage_begin(p);
-            mma_chunk(p, TM_ACC, aT, H, 128, 0);                  // value GNN layer 1
-            mma_stage_end(p);
-            mma_stage_begin(p);
-            mma_chunk(p, TM_ACC, aX, GH, 128, 0);                 // value GNN layer 2
-            mma_stage_end(p);
-            mma_stage_begin(p);
-            mma_chunk(p, TM_ACC, aT, H, PH, 0);                   // fc_policy.0
-            mma_stage_end(p);
-            mma_stage_begin(p);
-            mma_chunk(p, TM_ACC, aX, PH, (uint32_t)d.NAP, 0);     // fc_policy.3
-            mma_stage_end(p);
+            mma_stage_begin();                                   // fc_dynamic.0 on [h | onehot | attn]
+            if (issuer) mma_chunk(p, TM_ACC, aT, H, 128, 0);
+            if (issuer) mma_chunk(p, TM_ACC, aOne, uKA, 128, 1);
+            if (issuer) mma_chunk(p, TM_ACC, aX, H, 128, 1);
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
+            mma_stage_begin();
+            if (issuer) mma_chunk(p, TM_ACC, aT, H, 128, 0);                  // fc_dynamic.3
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
+            mma_stage_begin();
+            if (issuer) mma_chunk(p, TM_ACC, aX, H, 128, 0);                  // fc_dynamic.6
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
+            mma_stage_begin();                                   // reward GNN layer 1 on [h' | onehot]
+            if (issuer) mma_chunk(p, TM_ACC, aT, H, 128, 0);
+            if (issuer) mma_chunk(p, TM_ACC, aOne, uKA, 128, 1);
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
+            mma_stage_begin();
+            if (issuer) mma_chunk(p, TM_ACC, aX, GH, 128, 0);                 // reward GNN layer 2
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
+            mma_stage_begin();
+            if (issuer) mma_chunk(p, TM_ACC, aT, H, 128, 0);                  // value GNN layer 1
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
+            mma_stage_begin();
+            if (issuer) mma_chunk(p, TM_ACC, aX, GH, 128, 0);                 // value GNN layer 2
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
+            mma_stage_begin();
+            if (issuer) mma_chunk(p, TM_ACC, aT, H, PH, 0);                   // fc_policy.0
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
+            mma_stage_begin();
+            if (issuer) mma_chunk(p, TM_ACC, aX, PH, (uint32_t)d.NAP, 0);     // fc_policy.3
+            if (issuer) mma_stage_end(p);
+            __syncwarp();
         }
     } else {
         // ================================ epilogue warps ======================================================
@@ -635,8 +653,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
     TS();                           \
     fence_proxy_async();            \
     tc_fence_before();              \
-    named_bar_sync(5, NEPI);        \
-    if (tid == 0) mbar_arrive(&bar_ready); \
+    named_bar_sync(5, NEPI + 32);   \
     mbar_wait(&bar_mma, mma_phase); \
     mma_phase ^= 1;                 \
     tc_fence_after();               \

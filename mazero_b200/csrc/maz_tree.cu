@@ -285,7 +285,7 @@ int maz_tree_prepare_dev(maz_tree *t, const float *rewards, const float *values,
     if (!rewards || !values || !probs || !beta || (eps > 0 && !noises)) return set_err(MAZ_ERR_INVALID, "prepare: NULL input");
     DeviceGuard g(t->device);
     const unsigned seed_base = t->seed * 2333u + t->root_offset;  // cnode.cpp:574
-    k_seed<<<(t->L.B + 127) / 128, 128, 0, t->stream>>>(t->L, t->arena, seed_base);
+    k_seed<<<(t->L.B + 127) / 128, 128, 0, t->stream>>>(t->L, t->arena, seed_base);   // 4 warps x 32 trees per block
     k_prepare<<<tree_grid(t), tree_block(t), t->scratch_per_warp * t->wpb, t->stream>>>(
         t->L, t->arena, t->d_lam_pow, rewards, values, probs, beta, K, eps, noises, t->d_err);
     CU_TRY(cudaGetLastError());

@@ -12,22 +12,39 @@ __device__ __forceinline__ bool warp_tree(const TreeLayout &L, int &tree, int &l
     return tree < L.B;
 }
 
-// ---- std::mt19937(seed) for every tree (cnode.cpp:574, 186-189): one thread per tree ----------------
-__global__ void k_seed(TreeLayout L, char *arena, unsigned int seed_base)
+// ---- std::mt19937(seed) for every tree (cnode.cpp:574, 186-189) ----------------------------------------
+// The seeding recurrence is serial per tree, so a lane owns a tree; a warp transposes its 32 trees' words
+// through shared memory so that every global store is a full 128-byte line of ONE tree's state (the naive
+// one-thread-per-tree store pattern touched a different line per lane: 74 us per 1024 trees, profiles/).
+__global__ void __launch_bounds__(128) k_seed(TreeLayout L, char *arena, unsigned int seed_base)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= L.B) return;
-    char *tb = arena + (size_t)b * L.slab_bytes;
-    uint32_t *s = f_mt(L, tb);
+    __shared__ uint32_t tile[4][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = (blockIdx.x * 4 + warp) * 32;          // first tree of this warp
+    if (b0 >= L.B) return;
+    const int b = b0 + lane;
     uint32_t x = seed_base + (unsigned int)b;
-    s[0] = x;
-    for (int i = 1; i < kMtN; ++i) {
-        x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
-        s[i] = x;
+    for (int c = 0; c < kMtN; c += 32) {                  // 20 chunks of 32 words (the last one is 16 words)
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int w = c + i;
+            if (w > 0) x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)w;
+            tile[warp][lane][i] = x;                      // row = tree, column = word
+            if (w == kMtN - 1) break;
+        }
+        __syncwarp();
+        const int nw = min(32, kMtN - c);
+        for (int t = 0; t < 32; ++t) {                    // tree b0+t: lanes write its words c..c+nw-1 (one line)
+            if (b0 + t < L.B && lane < nw)
+                f_mt(L, arena + (size_t)(b0 + t) * L.slab_bytes)[c + lane] = tile[warp][t][lane];
+        }
+        __syncwarp();
     }
-    TreeHdr *h = f_hdr(tb);
-    h->mt_pos = kMtN;
-    h->err = 0;
+    if (b < L.B) {
+        TreeHdr *h = f_hdr(arena + (size_t)b * L.slab_bytes);
+        h->mt_pos = kMtN;
+        h->err = 0;
+    }
 }
 
 // ---- CTree_batch::prepare -> CTree::prepare (cnode.cpp:589-614, 205-222) ------------------------------
