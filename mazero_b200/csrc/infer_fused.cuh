@@ -69,7 +69,8 @@ __device__ __noinline__ void mma_chunk(Pipe &p, uint32_t dst, uint32_t a_addr, u
     const int c = p.c, s = c % NSLOT;
     mbar_wait(&p.full[s], (c / NSLOT) & 1);
     tc_fence_after();
-    if (!p.skip) issue_gemm(p.tmem + dst, a_addr, a_K, 0, p.slots + (uint32_t)s * SLOT_BYTES, a_K, 0, a_K, n_out, accum != 0);
+    if (!(p.skip & 2)) issue_gemm(p.tmem + dst, a_addr, a_K, 0, p.slots + (uint32_t)s * SLOT_BYTES, a_K, 0, a_K, n_out, accum != 0);
+    if (p.skip & 8) mbar_arrive(&p.empty[s]); else
     mma_commit(&p.empty[s]);     // slot reusable once these MMAs have completed
     p.c = c + 1;
 }
@@ -80,7 +81,10 @@ __device__ __forceinline__ void mma_stage_begin()
     named_bar_sync(5, NEPI_THREADS + 32);
     tc_fence_after();
 }
-__device__ __forceinline__ void mma_stage_end(Pipe &p) { mma_commit(p.mma); }
+__device__ __forceinline__ void mma_stage_end(Pipe &p)
+{
+    if (p.skip & 8) mbar_arrive(p.mma); else mma_commit(p.mma);   // (8: profiling, plain arrive instead of tcgen05.commit)
+}
 
 // ---- small per-thread helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack2(float a, float b)
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
         // ================================ MMA issuer ==========================================================
         {
             const bool issuer = (tid & 31) == 0;   // all 32 lanes take part in the named barrier, lane 0 issues
-            Pipe p{bar_full, bar_empty, &bar_mma, &bar_ready, smem_u32(sW), tmem, 0, 0, (d.dbg_flags & 2)};
+            Pipe p{bar_full, bar_empty, &bar_mma, &bar_ready, smem_u32(sW), tmem, 0, 0, (d.dbg_flags & (2 | 8))};
             const uint32_t uKA = (uint32_t)KA;
             mma_stage_begin();                                   // in-proj: W_in [h | onehot]
             if (issuer) mma_chunk(p, TM_ACC, aT, H, 128, 0);
