@@ -52,7 +52,7 @@ def _padrows(w, r):
 def supported(sd, num_agents, action_space_size, hidden):
     d = "dynamics_network."
     try:
-        return (hidden == H and num_agents <= 32 and action_space_size <= 48
+        return (hidden == H and num_agents <= 30 and action_space_size <= 48   # 30 = positional table (attention.py:35)
                 and f"{d}attention_stack.2.encoder.layers.2.linear1.weight" in sd
                 and f"{d}attention_stack.2.encoder.layers.3.linear1.weight" not in sd
                 and sd[f"{d}attention_stack.2.encoder.layers.0.linear1.weight"].shape == (H, H)

@@ -50,6 +50,16 @@ def test_cuda_tree_other_hyperparameters(cytree, oracle_built, rho, lam, K):
     assert_same(drive(ours, inp, K, mcts=mcts), drive(orc, inp, K, mcts=mcts), exact=True)
 
 
+@pytest.mark.parametrize("B,N,A,K,S", [(1, 1, 2, 1, 1), (3, 1, 2, 1, 120), (2, 32, 3, 2, 20), (5, 2, 200, 7, 15), (40, 2, 6, 3, 90)])
+def test_cuda_tree_edge_shapes(cytree, oracle_built, B, N, A, K, S):
+    """Single root / single simulation; K=1 chains (paths longer than a warp, logs longer than the register cache);
+    32 agents; large action spaces; many simulations."""
+    inp = Inputs(B, N, A, S, seed=B + S, mode="random")
+    ours = cytree.Tree_batch(B, N, A, K, S, 0.01, 41, 0.75, 0.8)
+    orc = oracle_built.OracleTreeBatch(B, N, A, K, S, 0.01, 41, 0.75, 0.8, kind="port")
+    assert_same(drive(ours, inp, K), drive(orc, inp, K), exact=True)
+
+
 def test_cuda_tree_long_rng_stream(cytree, oracle_built):
     """Many draws per expansion: crosses the 624-word mt19937 block boundary at every position parity."""
     B, N, A, K, S = 8, 13, 7, 9, 60
