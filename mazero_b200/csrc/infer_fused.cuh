@@ -100,7 +100,7 @@ __device__ __forceinline__ void store_cols(uint32_t tile, int row, int c, int K,
     for (int j = 0; j < NV; j += 8) {
         uint4 a;
         a.x = pack2(v[j], v[j + 1]); a.y = pack2(v[j + 2], v[j + 3]); a.z = pack2(v[j + 4], v[j + 5]); a.w = pack2(v[j + 6], v[j + 7]);
-        sts4(tile + chunk_off(row, (c + j) >> 3, K), a);
+        sts4(tile + operand_chunk_off(row, (c + j) >> 3, K, 128), a);   // swizzled for K % 64 == 0
     }
 }
 // v += vec (shared memory), with Blackwell's packed fp32 adds (FADD2)
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int N = d.N, KA = d.KA;
-    uint8_t *sX = smem;                               // 128 x 128 bf16
+    uint8_t *sX = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // 128 x 128 bf16, 1 KB aligned (swizzle atoms)
     uint8_t *sT = sX + operand_bytes(128, 128);       // 128 x 128 bf16
     uint8_t *sOne = sT + operand_bytes(128, 128);     // 128 x KA  bf16 (one-hot joint action)
     uint8_t *sW = sOne + operand_bytes(128, KA);      // weight ring, NSLOT x 32 KB

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128, 1) k_dbg_umma_gemm(const float *__restric
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_w, bar_mma;
     __shared__ uint32_t tmem_base_s;
-    uint8_t *sA = smem;                                   // 128 x K bf16
+    uint8_t *sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // 1 KB aligned (swizzled tiles)
     uint8_t *sW = smem + operand_bytes(128, K);           // N x K bf16
     const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128, 1) k_dbg_umma_gemm(const float *__restric
         v.y = *reinterpret_cast<uint32_t *>(&p1);
         v.z = *reinterpret_cast<uint32_t *>(&p2);
         v.w = *reinterpret_cast<uint32_t *>(&p3);
-        *reinterpret_cast<uint4 *>(sA + chunk_off(tid, k8, K)) = v;
+        *reinterpret_cast<uint4 *>(sA + operand_chunk_off(tid, k8, K, 128)) = v;
     }
     fence_proxy_async();
     __syncthreads();
@@ -81,7 +81,7 @@ extern "C" int maz_dbg_umma_gemm(const float *a, const void *w_packed, float *ou
 {
     if (!a || !w_packed || !out || n % 16 || k % 16 || n < 16 || n > 256 || k < 16 || k > 512)
         return set_last_error(1, "maz_dbg_umma_gemm: bad arguments");
-    const size_t dyn = operand_bytes(128, k) + operand_bytes(n, k) + 1024;
+    const size_t dyn = operand_bytes(128, k) + operand_bytes(n, k) + 2048;
     cudaError_t e = cudaFuncSetAttribute(k_dbg_umma_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return set_last_error(2, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     k_dbg_umma_gemm<<<1, 128, dyn, static_cast<cudaStream_t>(stream)>>>(a, static_cast<const __nv_bfloat16 *>(w_packed), out, n, k);

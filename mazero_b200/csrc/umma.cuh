@@ -217,6 +217,43 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- 128-byte-swizzled operand tiles (K a multiple of 64) ----------------------------------------------------
+// The no-swizzle layout above makes the tensor core fetch operands with shared-memory bank conflicts (measured:
+// ~1150 cycles per 128x128x128 GEMM instead of ~520).  SWIZZLE_128B, K-major: an "atom" is 8 rows x 64 bf16
+// (8 x 128 B = 1 KB, tile base 1 KB aligned); inside an atom the 16-byte chunk j of row r sits at chunk (j ^ r);
+// atoms are stored [K/64][rows/8]:
+//      byte_offset(r, k) = (k / 64) * rows * 128 + (r / 8) * 1024 + (r % 8) * 128 + (((k % 64) / 8) ^ (r % 8)) * 16 + (k % 8) * 2
+// Descriptor: layout_type 2 (SWIZZLE_128B), SBO = 1024, LBO unused (1).  A K = 16 step inside an atom advances the
+// start address by 32 B (the hardware applies the XOR to the generated addresses); the next 64-wide K block is
+// `rows * 128` bytes further.
+__device__ __forceinline__ uint32_t chunk_off_sw(uint32_t r, uint32_t k8, uint32_t rows)
+{
+    return (k8 >> 3) * rows * 128u + (r >> 3) * 1024u + (r & 7u) * 128u + (((k8 & 7u) ^ (r & 7u)) << 4);
+}
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (ignored for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;      // SBO: 8-row groups are 1 KB apart
+    d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// Measured on B200 (3m, 26 tiles): the swizzled layout is functionally correct (tests/test_infer_gpu.py) but did NOT
+// speed up the GEMM stages (105 us vs 93 us per launch: the per-chunk time is not operand-fetch bound and the
+// epilogue's address arithmetic grows), so it is compiled out.  Set MAZ_SWIZZLE to 1 to re-enable (and
+// mazero_b200.fused.SWIZZLE = True on the host side).
+#ifndef MAZ_SWIZZLE
+#define MAZ_SWIZZLE 0
+#endif
+__host__ __device__ constexpr bool use_swizzle(uint32_t K) { return MAZ_SWIZZLE && (K % 64u) == 0; }
+// operand-layout-aware chunk address: swizzled for K % 64 == 0, core-matrix layout otherwise
+__device__ __forceinline__ uint32_t operand_chunk_off(uint32_t r, uint32_t k8, uint32_t K, uint32_t rows)
+{
+    return use_swizzle(K) ? chunk_off_sw(r, k8, rows) : ((r >> 3) * ((K / 8) * 128u) + k8 * 128u + (r & 7u) * 16u);
+}
+
 // ---- operand tiles ----------------------------------------------------------------------------------------
 constexpr uint32_t kLBO = 128;
 __host__ __device__ constexpr uint32_t sbo_bytes(uint32_t K) { return (K / 8) * 128; }
@@ -230,19 +267,36 @@ __device__ __forceinline__ uint32_t chunk_off(uint32_t r, uint32_t k8, uint32_t 
 // Issue the K/16 MMAs of one GEMM stage: D[128 x N] (+)= A[128 x K] * W[N x K]^T.  ONE thread.
 // a_addr / w_addr: shared-memory byte addresses of operand tiles laid out for THEIR full K (a_K, w_K);
 // a_k0 / w_k0: first K index used from each (multiples of 16); kk: number of K elements (multiple of 16).
+// a_rows / w_rows: number of rows of the A tile (always 128) and of the W chunk (needed by the swizzled layout)
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t a_K, uint32_t a_k0, uint32_t w_addr,
-                                           uint32_t w_K, uint32_t w_k0, uint32_t kk, uint32_t N, bool accumulate)
+                                           uint32_t w_K, uint32_t w_k0, uint32_t kk, uint32_t N, bool accumulate,
+                                           uint32_t w_rows = 0)
 {
     const uint32_t idesc = instr_desc_bf16(128, N);
-    // descriptors of consecutive K=16 steps differ only in the start-address field: +256 B = +16 (address >> 4)
-    uint64_t da = smem_desc(a_addr + (a_k0 >> 3) * kLBO, kLBO, sbo_bytes(a_K));
-    uint64_t db = smem_desc(w_addr + (w_k0 >> 3) * kLBO, kLBO, sbo_bytes(w_K));
     uint32_t acc = accumulate ? 1u : 0u;
+    if (w_rows == 0) w_rows = N;
+    const bool sa = use_swizzle(a_K), sw = use_swizzle(w_K);
+    if (!sa && !sw) {
+        // descriptors of consecutive K=16 steps differ only in the start-address field: +256 B = +16 (address >> 4)
+        uint64_t da = smem_desc(a_addr + (a_k0 >> 3) * kLBO, kLBO, sbo_bytes(a_K));
+        uint64_t db = smem_desc(w_addr + (w_k0 >> 3) * kLBO, kLBO, sbo_bytes(w_K));
+#pragma unroll 1
+        for (uint32_t k = 0; k < kk; k += 16) {
+            mma_bf16(d_tmem, da, db, idesc, acc);
+            da += 16;
+            db += 16;
+            acc = 1u;
+        }
+        return;
+    }
 #pragma unroll 1
     for (uint32_t k = 0; k < kk; k += 16) {
+        const uint32_t ka = a_k0 + k, kw = w_k0 + k;
+        const uint64_t da = sa ? smem_desc_sw128(a_addr + (ka >> 6) * 128u * 128u + ((ka & 63u) >> 3) * 16u)
+                               : smem_desc(a_addr + (ka >> 3) * kLBO, kLBO, sbo_bytes(a_K));
+        const uint64_t db = sw ? smem_desc_sw128(w_addr + (kw >> 6) * w_rows * 128u + ((kw & 63u) >> 3) * 16u)
+                               : smem_desc(w_addr + (kw >> 3) * kLBO, kLBO, sbo_bytes(w_K));
         mma_bf16(d_tmem, da, db, idesc, acc);
-        da += 16;
-        db += 16;
         acc = 1u;
     }
 }

@@ -10,6 +10,7 @@ import torch
 from ._lib import check, lib
 
 NCHUNK = 32
+SWIZZLE = False   # must match MAZ_SWIZZLE in csrc/umma.cuh (128-byte swizzled operand tiles; measured slower)
 H, GH, PH, SUP = 128, 64, 32, 11
 
 
@@ -31,10 +32,19 @@ def _pad16(n):
 
 
 def pack_operand(w):
-    """[rows, K] fp32 -> bf16, K-major core-matrix layout: W.view(rows/8, 8, K/8, 8).permute(0, 2, 1, 3)."""
+    """[rows, K] fp32 -> bf16 in the kernels' shared-memory operand layout (csrc/umma.cuh).
+    K % 64 == 0: SWIZZLE_128B, K-major -- atoms of 8 rows x 64 elements stored [K/64][rows/8]; inside an atom the
+    16-byte chunk j of row r sits at chunk position j ^ (r % 8).
+    otherwise:   no swizzle, 8x8 core matrices: W.view(rows/8, 8, K/8, 8).permute(0, 2, 1, 3)."""
     r, k = w.shape
     assert r % 8 == 0 and k % 16 == 0, (r, k)
-    return w.to(torch.bfloat16).view(r // 8, 8, k // 8, 8).permute(0, 2, 1, 3).contiguous().view(-1)
+    wb = w.to(torch.bfloat16)
+    if SWIZZLE and k % 64 == 0:
+        t = wb.view(r // 8, 8, k // 64, 8, 8).permute(2, 0, 1, 3, 4)           # [kb, rg, r8, j, e]
+        ar = torch.arange(8, device=w.device)
+        src_chunk = ar[None, :] ^ ar[:, None]                                    # [r8, position] -> chunk j = position ^ r8
+        return t[:, :, ar[:, None], src_chunk, :].contiguous().view(-1)
+    return wb.view(r // 8, 8, k // 8, 8).permute(0, 2, 1, 3).contiguous().view(-1)
 
 
 def _padcols(w, k):

@@ -8,10 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def pack_operand(w):
-    """[rows, K] -> bf16 in the kernels' K-major core-matrix layout (mazero_b200/csrc/umma.cuh)."""
-    r, k = w.shape
-    return w.to(torch.bfloat16).view(r // 8, 8, k // 8, 8).permute(0, 2, 1, 3).contiguous()
+from mazero_b200.fused import pack_operand  # noqa: E402  (host-side packing under test as well)
 
 
 @pytest.mark.parametrize("n,k", [(128, 128), (64, 64), (256, 128), (16, 32), (128, 272), (32, 144)])
@@ -23,7 +20,7 @@ def test_umma_gemm_stage(built_lib, n, k):
     a = torch.randn(128, k, generator=g).to(dev)
     w = (torch.randn(n, k, generator=g) / k ** 0.5).to(dev)
     out = torch.full((128, n), float("nan"), device=dev)
-    wp = pack_operand(w)
+    wp = pack_operand(w).contiguous()
     _lib.check(_lib.lib.maz_dbg_umma_gemm(a.data_ptr(), wp.data_ptr(), out.data_ptr(), n, k,
                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
