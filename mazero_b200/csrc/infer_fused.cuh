@@ -70,8 +70,8 @@ __device__ __noinline__ void mma_chunk(Pipe &p, uint32_t dst, uint32_t a_addr, u
     mbar_wait(&p.full[s], (c / NSLOT) & 1);
     tc_fence_after();
     if (!(p.skip & 2)) issue_gemm(p.tmem + dst, a_addr, a_K, 0, p.slots + (uint32_t)s * SLOT_BYTES, a_K, 0, a_K, n_out, accum != 0);
-    if (p.skip & 8) mbar_arrive(&p.empty[s]); else
-    mma_commit(&p.empty[s]);     // slot reusable once these MMAs have completed
+    // (the ring slot is released by epilogue thread 0 after the stage's bar_mma completes: one tcgen05.commit per
+    //  stage instead of one per chunk on this thread's serial path)
     p.c = c + 1;
 }
 // "operands ready" hand-off: the 512 epilogue threads and the 32 lanes of the MMA warp meet on hardware named
@@ -275,13 +275,72 @@ __device__ __noinline__ void epi_ln128(uint32_t trow, uint32_t tcol, uint32_t sb
     if (store_x) tmem_st_wait();
 }
 
-// scaled dot-product attention over the N agents of my root; each column part owns HPP heads; online softmax.
+// scaled dot-product attention over the N agents of my root; each column part owns HPP heads.
 // sb: shared address of [bq | bk | bv] (3 x 128 floats).  Output (bf16) into the operand tile.
+// Small teams (N <= 4, e.g. 3m): two-phase softmax with everything unrolled -- all N score chains are independent
+// (instruction-level parallelism; the online form below serialises max / exp / rescale per key) and the dot
+// products use packed fp32 FMAs.  Larger N: one pass, online softmax.
+template <int NN>
+__device__ __forceinline__ void attention_head_small(uint32_t trow, uint32_t sb, int hh, int root_lane0, uint32_t tile, int row)
+{
+    float q[16], k[16], v[16];
+    tmem_ld16(trow + TM_Q + hh * HD, q);
+    tmem_ld16(trow + TM_K + hh * HD, k);
+    tmem_ld16(trow + TM_V + hh * HD, v);
+    add_svec(q, sb + 4 * (hh * HD));
+    add_svec(k, sb + 4 * (H + hh * HD));
+    add_svec(v, sb + 4 * (2 * H + hh * HD));
+    float s[NN];
+#pragma unroll
+    for (int j = 0; j < NN; ++j) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            const float2 kj = make_float2(__shfl_sync(0xffffffffu, k[i], root_lane0 + j), __shfl_sync(0xffffffffu, k[i + 1], root_lane0 + j));
+            acc = __ffma2_rn(make_float2(q[i], q[i + 1]), kj, acc);
+        }
+        s[j] = (acc.x + acc.y) * 0.25f;   // 1/sqrt(head_dim)
+    }
+    float m = s[0];
+#pragma unroll
+    for (int j = 1; j < NN; ++j) m = fmaxf(m, s[j]);
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < NN; ++j) { s[j] = __expf(s[j] - m); l += s[j]; }
+    const float inv = 1.f / l;
+    float2 o2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o2[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NN; ++j) {
+        const float pj = s[j] * inv;
+        const float2 p2 = make_float2(pj, pj);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 vj = make_float2(__shfl_sync(0xffffffffu, v[2 * i], root_lane0 + j), __shfl_sync(0xffffffffu, v[2 * i + 1], root_lane0 + j));
+            o2[i] = __ffma2_rn(p2, vj, o2[i]);
+        }
+    }
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[2 * i] = o2[i].x; o[2 * i + 1] = o2[i].y; }
+    store_cols(tile, row, hh * HD, H, o);
+}
+
 __device__ __noinline__ void epi_attention(uint32_t trow, uint32_t sb, int N, int root_lane0, uint32_t tile)
 {
     const Thr t;
 #pragma unroll 1
     for (int hh = t.part * HPP; hh < (t.part + 1) * HPP; ++hh) {
+        if (N <= 4) {   // warp-uniform
+            switch (N) {
+                case 1: attention_head_small<1>(trow, sb, hh, root_lane0, tile, t.row); break;
+                case 2: attention_head_small<2>(trow, sb, hh, root_lane0, tile, t.row); break;
+                case 3: attention_head_small<3>(trow, sb, hh, root_lane0, tile, t.row); break;
+                default: attention_head_small<4>(trow, sb, hh, root_lane0, tile, t.row); break;
+            }
+            continue;
+        }
         float q[16], k[16], v[16], o[16];
         tmem_ld16(trow + TM_Q + hh * HD, q);
         tmem_ld16(trow + TM_K + hh * HD, k);
@@ -647,13 +706,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
         const int valid = (rl < rpw) && (root < d.B);
         const int root_lane0 = (rl < rpw) ? rl * N : 0;   // first lane of my root inside the warp
         uint32_t mma_phase = 0;
+        int c_ep = 0;   // chunks consumed so far (ring-slot release bookkeeping)
         const bool do_epi = !(d.dbg_flags & 1);
         int ts_n = 0;
         const bool ts_on = d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0;
 #define TS() \
     if (ts_on && ts_n < 256) d.dbg_clock[ts_n++] = clock64();
 // publish my operand writes to the async proxy, tell the MMA warp, wait for the stage's accumulator
-#define HANDOFF()                   \
+#define HANDOFF(nchunks)            \
     TS();                           \
     fence_proxy_async();            \
     tc_fence_before();              \
@@ -661,6 +721,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
     mbar_wait(&bar_mma, mma_phase); \
     mma_phase ^= 1;                 \
     tc_fence_after();               \
+    if (tid == 0) {                 \
+        for (int i__ = 0; i__ < (nchunks); ++i__) mbar_arrive(&bar_empty[(c_ep + i__) % NSLOT]); \
+    }                               \
+    c_ep += (nchunks);              \
     TS();
 
         // ---- gather the parent's hidden state and build the one-hot action operand ------------------------
@@ -681,56 +745,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
         }
         mbar_wait(&bar_vec, 0);   // parameters resident
         // ---- attention_stack[0..1]: x0 = relu(W_in [h | onehot] + b) + positional table --------------------
-        HANDOFF();
+        HANDOFF(2);
         if (do_epi) epi_inproj(trow, aP + 4 * d.o_bin, aP + 4 * (d.o_pos + agent * H), aX);
         // ---- 3 x post-LN TransformerEncoderLayer over the agent axis (attention.py:36-43) ---------------------
 #pragma unroll 1
         for (int l = 0; l < NLAYER; ++l) {
             const uint32_t lv = aP + 4 * (d.o_layer + l * 1280);   // bq bk bv bo g1 be1 b1 b2 g2 be2
-            HANDOFF();
+            HANDOFF(3);
             if (do_epi) epi_attention(trow, lv, N, root_lane0, aT);
-            HANDOFF();
+            HANDOFF(1);
             if (do_epi) epi_ln128(trow, TM_X, lv + 4 * 384, lv + 4 * 512, lv + 4 * 640, 0, 1, aX, aRed);     // norm1
-            HANDOFF();
+            HANDOFF(1);
             if (do_epi) epi_bias_relu(trow, lv + 4 * 768, aT);                                                 // relu(linear1)
-            HANDOFF();
+            HANDOFF(1);
             if (do_epi) epi_ln128(trow, TM_X, lv + 4 * 896, lv + 4 * 1024, lv + 4 * 1152, 0, 1, aX, aRed);   // norm2
         }
         // ---- fc_dynamic: Linear-LN-ReLU, Linear-LN-ReLU, Linear; residual (model.py:262-268) ------------------
         const uint32_t dv = aP + 4 * d.o_dyn;
         gather_hidden(hrow, valid, aT);   // h (bf16) back into sT; sX holds the attention output
-        HANDOFF();
+        HANDOFF(3);
         if (do_epi) epi_ln128(trow, TM_ACC, dv, dv + 4 * 128, dv + 4 * 256, 1, 0, aT, aRed);
-        HANDOFF();
+        HANDOFF(1);
         if (do_epi) epi_ln128(trow, TM_ACC, dv + 4 * 384, dv + 4 * 512, dv + 4 * 640, 1, 0, aX, aRed);
-        HANDOFF();
+        HANDOFF(1);
         {
             float *nh = d.next_hidden + (valid ? (size_t)root * (N * H) + (size_t)agent * H : 0);
             if (do_epi) epi_next_hidden(trow, dv + 4 * 768, hrow, nh, valid, aT);
         }
         // ---- reward head: GraphNetNN on [next_hidden | onehot] (model.py:270-277) -----------------------------
         const uint32_t rv = aP + 4 * d.o_rg;
-        HANDOFF();
+        HANDOFF(2);
         if (do_epi) epi_gnn(trow, rv, N, root_lane0, 0, aX, aRed, 0);
-        HANDOFF();
+        HANDOFF(1);
         {
             const float r = !do_epi ? 0.f : epi_gnn(trow, rv + 4 * 128, N, root_lane0, 1, 0, aRed, aX);   // sX is free: scratch
             if (valid && agent == 0 && t.part == 0) d.reward[root] = r;
         }
         // ---- value head: GraphNetNN on next_hidden (model.py:359) ----------------------------------------------
         const uint32_t vv = aP + 4 * d.o_vg;
-        HANDOFF();
+        HANDOFF(1);
         if (do_epi) epi_gnn(trow, vv, N, root_lane0, 0, aX, aRed, 0);
-        HANDOFF();
+        HANDOFF(1);
         {
             const float val = !do_epi ? 0.f : epi_gnn(trow, vv + 4 * 128, N, root_lane0, 1, 0, aRed, aX);
             if (valid && agent == 0 && t.part == 0) d.value[root] = val;
         }
         // ---- policy head + the driver's softmax / beta ------------------------------------------------------------
         const uint32_t pv = aP + 4 * d.o_pol;
-        HANDOFF();
+        HANDOFF(1);
         if (do_epi) epi_policy_hidden(trow, pv, aX, aRed);
-        HANDOFF();
+        HANDOFF(1);
         if (do_epi && t.part == 0) epi_policy_out(d, trow, pv + 4 * 96, valid, root, agent);
         TS();
 #undef HANDOFF
