@@ -383,7 +383,7 @@ __device__ __noinline__ void epi_next_hidden(uint32_t trow, uint32_t sb, const f
     if (valid) {
 #pragma unroll
         for (int i = 0; i < CP; i += 4) {
-            const float4 h = *reinterpret_cast<const float4 *>(hrow + c + i);
+            const float4 h = __ldcg(reinterpret_cast<const float4 *>(hrow + c + i));
             v[i] += h.x; v[i + 1] += h.y; v[i + 2] += h.z; v[i + 3] += h.w;
             *reinterpret_cast<float4 *>(nh + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
@@ -574,7 +574,7 @@ __device__ __noinline__ void gather_hidden(const float *__restrict__ hrow, int v
     float v[CP];
 #pragma unroll
     for (int i = 0; i < CP; i += 4) {
-        const float4 h = valid ? *reinterpret_cast<const float4 *>(hrow + c + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 h = valid ? __ldcg(reinterpret_cast<const float4 *>(hrow + c + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         v[i] = h.x; v[i + 1] = h.y; v[i + 2] = h.z; v[i + 3] = h.w;
     }
     store_cols(tile, t.row, c, H, v);
@@ -727,13 +727,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
     c_ep += (nchunks);              \
     TS();
 
+        // PDL: everything up to here (and the producer warp's weight streaming) may overlap the tail of the tree kernel
+        // that produces idx_x / actions; wait for it before touching its outputs or the pool.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        // Only NOW may the next tree kernel start: its pre-wait section prefetches tree state, which the tree kernel
+        // we just waited for was still writing.  (The tree kernel itself triggers at its start: this kernel's
+        // pre-wait section touches nothing but constants.)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         // ---- gather the parent's hidden state and build the one-hot action operand ------------------------
         const float *hrow = d.pool;
         int my_action = -1;
         if (valid) {
-            const int ix = d.idx_x ? d.idx_x[root] : 0;
+            const int ix = d.idx_x ? __ldcg(d.idx_x + root) : 0;   // .cg: produced by the kernel we may have overlapped (PDL)
             hrow = d.pool + ((size_t)ix * d.B + root) * (size_t)(N * H) + (size_t)agent * H;
-            my_action = d.actions[(size_t)root * N + agent];
+            my_action = __ldcg(d.actions + (size_t)root * N + agent);
         }
         gather_hidden(hrow, valid, aT);
         if (t.part * 16 < KA) {

@@ -12,7 +12,7 @@ using namespace maz;
 using namespace maz::umma;
 
 extern "C" const char *maz_last_error(void);
-namespace maz { int set_last_error(int code, const std::string &msg); }
+namespace maz { int set_last_error(int code, const std::string &msg); bool pdl_enabled(); int pdl_mask(); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Self-test kernel: one GEMM stage exactly as the fused kernel runs it.
@@ -108,8 +108,19 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
     }
     const int roots_per_tile = 4 * (32 / d->N);
     const int tiles = (d->B + roots_per_tile - 1) / roots_per_tile;
-    fused::k_recurrent_inference<<<tiles, fused::NTHREADS, dyn, static_cast<cudaStream_t>(stream)>>>(*d);
-    cudaError_t e = cudaGetLastError();
+    // programmatic dependent of the tree kernel: TMEM allocation, barrier set-up and the weight / parameter
+    // streaming overlap the predecessor's tail; the epilogue warps call griddepcontrol.wait before they read it
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.blockDim = dim3(fused::NTHREADS);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (maz::pdl_mask() & 1) ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fused::k_recurrent_inference, *d);
     if (e != cudaSuccess) return set_last_error(2, std::string("k_recurrent_inference: ") + cudaGetErrorString(e));
     return 0;
 }

@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -22,6 +23,17 @@ static int set_err(int code, const std::string &msg)
 }
 namespace maz {
 int set_last_error(int code, const std::string &msg) { return set_err(code, msg); }  // shared with maz_infer.cu
+// Programmatic dependent launch between the two kernels of the on-device loop: MAZ_PDL bit 0 = inference kernel,
+// bit 1 = tree kernel.  OFF by default: measured on B200 inside the CUDA graph it buys nothing (5.668 ms vs 5.664 ms
+// per 1024 x 50 search), and it needs care: an early-resident dependent grid can hit STALE L1 lines of buffers that
+// the predecessor is still writing (the per-simulation reward / value / probs / beta buffers are re-used every
+// simulation) -- data produced by the predecessor is therefore read with ld.global.cg (L2) in both kernels.
+int pdl_mask()
+{
+    static const int m = [] { const char *e = getenv("MAZ_PDL"); return e ? atoi(e) : 0; }();
+    return m;
+}
+bool pdl_enabled() { return pdl_mask() != 0; }
 }
 
 #define CU_TRY(expr)                                                                                          \
@@ -334,10 +346,21 @@ int maz_tree_expansion_backup_selection_dev(maz_tree *t, int hidx, float discoun
     int rc = maz_tree_set_puct(t, c_base, c_init);
     if (rc) return rc;
     DeviceGuard g(t->device);
-    k_expand_backup_select<<<tree_grid(t), tree_block(t), t->scratch_per_warp * t->wpb, t->stream>>>(
-        t->L, t->arena, t->d_lam_pow, hidx, discount, K, rewards, values, probs, beta, t->d_logterm, t->d_sqrtn, t->table_len,
-        idx_x, idx_y, act, t->d_err);
-    CU_TRY(cudaGetLastError());
+    // launched as a programmatic dependent of the inference kernel: the tree-state prefetch overlaps its tail
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = tree_grid(t);
+    cfg.blockDim = tree_block(t);
+    cfg.dynamicSmemBytes = t->scratch_per_warp * t->wpb;
+    cfg.stream = t->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (maz::pdl_mask() & 2) ? 1 : 0;
+    const float *lam = t->d_lam_pow, *lt = t->d_logterm;
+    const double *sq = t->d_sqrtn;
+    CU_TRY(cudaLaunchKernelEx(&cfg, k_expand_backup_select, t->L, t->arena, lam, hidx, discount, K, rewards, values, probs, beta,
+                              lt, sq, t->table_len, idx_x, idx_y, act, t->d_err));
     return MAZ_OK;
 }
 

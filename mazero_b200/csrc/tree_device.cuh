@@ -44,6 +44,12 @@ MAZ_FIELD(float, f_vsval, off_vsval)
 
 __device__ __forceinline__ TreeHdr *f_hdr(char *tb) { return reinterpret_cast<TreeHdr *>(tb); }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may start while its predecessor in the stream is still running; griddep_wait() blocks until the predecessor has
+// completed and its writes are visible (a no-op without the attribute); griddep_launch() lets the successor start.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // order-preserving float <-> uint map (for redux.sync min/max on floats)
 __device__ __forceinline__ uint32_t f2ord(float f)
 {
@@ -196,9 +202,11 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
 {
     const int N = L.N, A = L.A, NA = N * A;
 
+    // .cg loads (L2 only): under programmatic dependent launch this kernel can already be resident on an SM whose
+    // L1 still holds the previous simulation's lines of these (re-used) buffers
     for (int t = lane; t < NA; t += 32) {
-        sc.beta[t] = beta[t];
-        sc.probs[t] = probs[t];
+        sc.beta[t] = __ldcg(beta + t);
+        sc.probs[t] = __ldcg(probs + t);
     }
     __syncwarp();
 
@@ -290,7 +298,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
             beta_prob = __fmul_rn(beta_prob, pb);
             pred_prob = __fmul_rn(pred_prob, pp);
             if (eps > 0) {
-                float p = __fadd_rn(__fmul_rn(pp, ome), __fmul_rn(__ldg(noises + i * A + a), eps));
+                float p = __fadd_rn(__fmul_rn(pp, ome), __fmul_rn(__ldcg(noises + i * A + a), eps));
                 prior = __fmul_rn(prior, p);
             } else {
                 prior = __fmul_rn(prior, pp);

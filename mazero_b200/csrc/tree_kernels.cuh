@@ -247,10 +247,12 @@ __global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ lo
 constexpr int kLogRegs = 8;   // 8 x 32 log entries cached in registers; longer logs: tail scanned from memory
 
 __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ lam_pow,
-                                                     int hidx, float discount, int K, float reward_in, float value,
+                                                     int hidx, float discount, int K, const float *__restrict__ reward_ptr,
+                                                     const float *__restrict__ value_ptr,
                                                      const float *__restrict__ probs, const float *__restrict__ beta,
                                                      const ExpandScratch &sc, int lane, int *g_err)
 {
+    griddep_launch();   // PDL: the next kernel (inference of the next simulation) may start its prologue now
     int tot_nodes = h->tot_nodes, log_len = h->log_len, mt_pos = h->mt_pos, n_expanded = h->n_expanded, err = h->err;
     const int len = h->path_len;
     const int log_len0 = log_len;
@@ -295,6 +297,10 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
         if (fast && lane >= 1 && lane <= len) my_ppv = f_pred_value(L, tb)[prev];   // parent's pred_value
     }
 
+    // PDL: everything above only touched this tree's own state (written by the previous tree kernel, long
+    // complete); the network outputs of THIS simulation are produced by the kernel we may be overlapping with.
+    griddep_wait();
+    const float reward_in = __ldcg(reward_ptr), value = __ldcg(value_ptr);   // L2 loads, see expand_node
     expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, reward_in, value, probs, beta, K, 0.0f, nullptr, sc,
                 lane, draws_pre);
 
@@ -370,7 +376,7 @@ __global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restri
     char *tb = arena + (size_t)tree * L.slab_bytes;
     const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
     const size_t NA = (size_t)L.N * L.A;
-    expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards[tree], values[tree], probs + tree * NA,
+    expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
                          beta + tree * NA, sc, lane, g_err);
 }
 
@@ -388,7 +394,7 @@ __global__ void k_expand_backup_select(TreeLayout L, char *arena, const float *_
     char *tb = arena + (size_t)tree * L.slab_bytes;
     const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
     const size_t NA = (size_t)L.N * L.A;
-    expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards[tree], values[tree], probs + tree * NA,
+    expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
                          beta + tree * NA, sc, lane, g_err);
     __syncwarp();
     select_path_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
