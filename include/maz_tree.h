@@ -124,6 +124,9 @@ int maz_tree_readout_dev(maz_tree *t, float discount, float *values, int *margin
  * sum of selection depths so far -- the d-bar / C-bar inputs of the roofline byte formula. */
 int maz_tree_stats(maz_tree *t, int *tot_nodes /* (B,) */, int *last_search_len /* (B,) */,
                    long long *sum_search_len /* scalar */, long long *sum_expanded /* scalar */);
+/* profiling: SM-cycle timestamps of tree 0's phases in the next kernels are written to `dev_clock64` (device
+ * pointer to 64 long longs), NULL switches it off */
+int maz_tree_set_debug_clock(maz_tree *t, long long *dev_clock64);
 /* bytes of HBM held by the handle's arena */
 size_t maz_tree_arena_bytes(const maz_tree *t);
 

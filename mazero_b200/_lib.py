@@ -42,6 +42,7 @@ SIGNATURES = {
     "maz_tree_readout": (C.c_int, [C.c_void_p, C.c_float] + [C.c_void_p] * 15),
     "maz_tree_readout_dev": (C.c_int, [C.c_void_p, C.c_float] + [C.c_void_p] * 15),
     "maz_tree_stats": (C.c_int, [C.c_void_p, _i32p, _i32p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "maz_tree_set_debug_clock": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maz_tree_arena_bytes": (C.c_size_t, [C.c_void_p]),
     # include/maz_infer.h
     "maz_dbg_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -66,6 +66,7 @@ struct maz_tree {
     float *d_lam_pow = nullptr;   // lam_pow[d], d = 0..S+1 (utils.cpp:25-26 running fp32 product)
     float *d_logterm = nullptr;   // (float)(log((n + c_base + 1)/c_base) + c_init), n = 0..S+1
     double *d_sqrtn = nullptr;    // sqrt((double)n)
+    float *d_pbc = nullptr;       // pb_c[n][visit] (cnode.cpp:313-314 evaluated on the host for every (n, visit))
     int table_len = 0;
     bool puct_set = false;
     float c_base = 0, c_init = 0;
@@ -217,6 +218,7 @@ void maz_tree_destroy(maz_tree *t)
     cudaFree(t->d_lam_pow);
     cudaFree(t->d_logterm);
     cudaFree(t->d_sqrtn);
+    cudaFree(t->d_pbc);
     cudaFree(t->d_err);
     cudaFree(t->d_sums);
     cudaFree(t->s_rewards);
@@ -279,6 +281,22 @@ int maz_tree_set_puct(maz_tree *t, float c_base, float c_init)
     }
     CU_TRY(cudaMemcpyAsync(t->d_logterm, lt.data(), lt.size() * sizeof(float), cudaMemcpyHostToDevice, t->stream));
     CU_TRY(cudaMemcpyAsync(t->d_sqrtn, sq.data(), sq.size() * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+    // the whole prior coefficient as a 2-D table: fp64 divide + multiply cost ~600 cycles per tree level on the device
+    // (few fp64 units), the table is one L1/L2-resident float load.  Same IEEE double operations, evaluated here.
+    const size_t T = (size_t)t->table_len;
+    if (T * T <= (size_t)4 << 20) {
+        std::vector<float> pbc(T * T);
+        for (size_t n = 0; n < T; ++n)
+            for (size_t v = 0; v < T; ++v) pbc[n * T + v] = (float)((double)lt[n] * (sq[n] / (double)(v + 1)));
+        if (!t->d_pbc) CU_TRY(cudaMalloc(&t->d_pbc, sizeof(float) * T * T));
+        CU_TRY(cudaMemcpyAsync(t->d_pbc, pbc.data(), pbc.size() * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+        CU_TRY(cudaStreamSynchronize(t->stream));
+        t->L.pbc_table = t->d_pbc;
+        t->L.pbc_dim = (int)T;
+    } else {
+        t->L.pbc_table = nullptr;
+        t->L.pbc_dim = 0;
+    }
     CU_TRY(cudaStreamSynchronize(t->stream));
     t->c_base = c_base;
     t->c_init = c_init;
@@ -536,6 +554,13 @@ int maz_tree_stats(maz_tree *t, int *tot_nodes, int *last_len, long long *sum_le
     CU_TRY(cudaStreamSynchronize(t->stream));
     if (sum_len) *sum_len = (long long)sums[0];
     if (sum_expanded) *sum_expanded = (long long)sums[1];
+    return MAZ_OK;
+}
+
+int maz_tree_set_debug_clock(maz_tree *t, long long *p)
+{
+    if (!t) return set_err(MAZ_ERR_INVALID, "null handle");
+    t->L.dbg_clock = p;
     return MAZ_OK;
 }
 

@@ -50,6 +50,12 @@ __device__ __forceinline__ TreeHdr *f_hdr(char *tb) { return reinterpret_cast<Tr
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// profiling: phase timestamps of tree 0 (lane 0) when TreeLayout::dbg_clock is set
+#define MAZ_TS(L, tree, lane, slot)                                                          \
+    do {                                                                                     \
+        if ((L).dbg_clock && (tree) == 0 && (lane) == 0) (L).dbg_clock[(slot)] = clock64(); \
+    } while (0)
+
 // order-preserving float <-> uint map (for redux.sync min/max on floats)
 __device__ __forceinline__ uint32_t f2ord(float f)
 {
@@ -198,7 +204,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
                                            int &err, int slot, int hidx, float reward, float value,
                                            const float *__restrict__ probs, const float *__restrict__ beta,
                                            int K, float eps, const float *__restrict__ noises,
-                                           const ExpandScratch &sc, int lane, bool draws_prefetched = false)
+                                           const ExpandScratch &sc, int lane, bool draws_prefetched = false, int dbg_tree = -1)
 {
     const int N = L.N, A = L.A, NA = N * A;
 
@@ -209,22 +215,49 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
         sc.probs[t] = __ldcg(probs + t);
     }
     __syncwarp();
+    MAZ_TS(L, dbg_tree, lane, 11);
 
     if (A >= 2) {
-        // std::discrete_distribution::param_type::_M_initialize (random.tcc:2657-2678): sequential fp64
-        for (int i = lane; i < N; i += 32) {
-            const float *bi = sc.beta + i * A;
-            double sum = 0.0;
-            for (int a = 0; a < A; ++a) sum = __dadd_rn(sum, (double)bi[a]);
-            double run = 0.0;
-            for (int a = 0; a < A; ++a) {
-                double p = __ddiv_rn((double)bi[a], sum);
-                run = (a == 0) ? p : __dadd_rn(run, p);
-                sc.cp[i * A + a] = run;
+        // std::discrete_distribution::param_type::_M_initialize (random.tcc:2657-2678).  The two running sums are
+        // sequential fp64 chains per agent (their order is observable), but the A divisions p_a = w_a / sum are
+        // independent: one lane per (agent, action) does them in parallel (an fp64 divide is ~300 cycles of latency).
+        if (N <= 32) {
+            double *sums = reinterpret_cast<double *>(sc.keys);   // 32 x 8 bytes, free until the hash keys are built
+            if (lane < N) {                                 // pass 1: sum_i = accumulate(w_i, 0.0), lane i
+                const float *bi = sc.beta + lane * A;
+                double sum = 0.0;
+                for (int a = 0; a < A; ++a) sum = __dadd_rn(sum, (double)bi[a]);
+                sums[lane] = sum;
             }
-            sc.cp[i * A + A - 1] = 1.0;
+            __syncwarp();
+            for (int t = lane; t < NA; t += 32)             // pass 2: every quotient, in parallel
+                sc.cp[t] = __ddiv_rn((double)sc.beta[t], sums[t / A]);
+            __syncwarp();
+            if (lane < N) {                                 // pass 3: partial_sum, lane i; last entry forced to 1.0
+                double *ci = sc.cp + lane * A;
+                double run = ci[0];
+                for (int a = 1; a < A; ++a) {
+                    run = __dadd_rn(run, ci[a]);
+                    ci[a] = run;
+                }
+                ci[A - 1] = 1.0;
+            }
+        } else {
+            for (int i = lane; i < N; i += 32) {
+                const float *bi = sc.beta + i * A;
+                double sum = 0.0;
+                for (int a = 0; a < A; ++a) sum = __dadd_rn(sum, (double)bi[a]);
+                double run = 0.0;
+                for (int a = 0; a < A; ++a) {
+                    double p = __ddiv_rn((double)bi[a], sum);
+                    run = (a == 0) ? p : __dadd_rn(run, p);
+                    sc.cp[i * A + a] = run;
+                }
+                sc.cp[i * A + A - 1] = 1.0;
+            }
         }
         __syncwarp();
+        MAZ_TS(L, dbg_tree, lane, 12);
         // K*N draws in (k major, agent minor) order (cnode.cpp:251-259); 2 raw outputs per draw
         const int KN = K * N;
         uint32_t *mt = f_mt(L, tb);
@@ -251,6 +284,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
         __syncwarp();
     }
 
+    MAZ_TS(L, dbg_tree, lane, 13);
     // hash key of sample k = lane (cnode.cpp:258): key = key*23333 + a, C `long` wrap-around
     unsigned long long ukey = 0;
     if (lane < K) {
@@ -262,23 +296,20 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
     const long long key = (long long)ukey;
     // std::map semantics: count per distinct key, action vector of the LAST sample with that key,
     // children in ascending key order.
-    int cnt = 0;
-    bool is_last = lane < K;
-    for (int j = 0; j < K; ++j) {
-        long long kj = sc.keys[j];
-        if (lane < K && kj == key) {
-            ++cnt;
-            if (j > lane) is_last = false;
-        }
-    }
+    // lanes >= K get a private key so that they never match a real sample
+    const unsigned same = __match_any_sync(MAZ_FULL, (lane < K) ? key : (long long)(0x7fffffffffff0000ll + lane));
+    const int cnt = __popc(same);
+    const bool is_last = (lane < K) && (31 - __clz(same) == lane);
     const unsigned lastmask = __ballot_sync(MAZ_FULL, is_last);
     int rank = 0;
+#pragma unroll 4
     for (int j = 0; j < K; ++j) {
         long long kj = sc.keys[j];
         if (((lastmask >> j) & 1u) && kj < key) ++rank;
     }
     const int C = __popc(lastmask);
     const int base = tot_nodes;
+    MAZ_TS(L, dbg_tree, lane, 14);
     if (base + C > L.P) {
         err = kErrPoolExhausted;
         return 0;
@@ -330,6 +361,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
     tot_nodes = base + C;
     n_expanded += 1;
     __syncwarp();
+    MAZ_TS(L, dbg_tree, lane, 15);
     return C;
 }
 
@@ -360,15 +392,14 @@ __device__ __forceinline__ void vs_scan_entry(VsScan &r, uint32_t tag, uint32_t 
 // Apply the update given the per-lane scan.  wsum / wtot are the node's weighted_sum / tot_weight
 // (warp-uniform registers, written back by the caller).
 __device__ __forceinline__ void vs_apply(const TreeLayout &L, char *tb, int &log_len, int &err, float &wsum, float &wtot,
-                                         uint32_t tag, int depth, float key, const float *__restrict__ lam_pow, int lane,
-                                         const VsScan &r)
+                                         uint32_t tag, float lp, float key, int lane, const VsScan &r)
 {
     uint32_t *vk = f_vskey(L, tb);
     float *vv = f_vsval(L, tb);
     const int cnt = __reduce_add_sync(MAZ_FULL, r.cnt);
     const int nbig = __reduce_add_sync(MAZ_FULL, r.nbig);
     const int nsmall = cnt - nbig;
-    const float lp = lam_pow[depth];
+    // lp = lam_pow[depth] (utils.cpp:25-26)
     // size_lim = max(1, (int)ceil(count * (1 - quantile)))  (utils.cpp:31; float product, ceil)
     int lim = __float2int_ru(__fmul_rn((float)(cnt + 1), L.one_minus_rho));
     if (lim < 1) lim = 1;
@@ -434,7 +465,7 @@ __device__ __forceinline__ void vs_update(const TreeLayout &L, char *tb, int &lo
     VsScan r;
     vs_scan_init(r);
     for (int e = lane; e < log_len; e += 32) vs_scan_entry(r, tag, vk[e], vv[e], e);
-    vs_apply(L, tb, log_len, err, wsum, wtot, tag, depth, key, lam_pow, lane, r);
+    vs_apply(L, tb, log_len, err, wsum, wtot, tag, lam_pow[depth], key, lane, r);
     __syncwarp();
 }
 

@@ -153,7 +153,9 @@ __device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb
             if (lane < C) {
                 // pb_c = log((n + c_base + 1)/c_base) + c_init   [float <- double]   (host table)
                 // pb_c *= sqrt(n) / (visit + 1)                   [float <- double product]
-                const float pb_c = (float)__dmul_rn((double)logterm[n], __ddiv_rn(sqrtn[n], (double)(cvis + 1)));
+                const float pb_c = (L.pbc_dim > 0)
+                                       ? L.pbc_table[(size_t)n * L.pbc_dim + min(cvis, L.pbc_dim - 1)]
+                                       : (float)__dmul_rn((double)logterm[n], __ddiv_rn(sqrtn[n], (double)(cvis + 1)));
                 const float prior_score = __fmul_rn(pb_c, prior);
                 float v = 0.0f;
                 if (cvis != 0) v = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), pq);
@@ -194,7 +196,9 @@ __device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb
                 } else {
                     r = mt_next(mt, mt_pos, lane);
                 }
-                ci = (int)__fns(listmask, 0, (int)(r % (uint32_t)nl) + 1);
+                uint32_t mrem = listmask;                   // drop the (r % nl) lowest candidates, take the next one
+                for (uint32_t skip = r % (uint32_t)nl; skip > 0; --skip) mrem &= mrem - 1;
+                ci = __ffs(mrem) - 1;
             }
         }
         // descend: the chosen child's header is in lane ci's registers
@@ -250,8 +254,9 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
                                                      int hidx, float discount, int K, const float *__restrict__ reward_ptr,
                                                      const float *__restrict__ value_ptr,
                                                      const float *__restrict__ probs, const float *__restrict__ beta,
-                                                     const ExpandScratch &sc, int lane, int *g_err)
+                                                     const ExpandScratch &sc, int lane, int *g_err, int tree = -1)
 {
+    MAZ_TS(L, tree, lane, 0);
     griddep_launch();   // PDL: the next kernel (inference of the next simulation) may start its prologue now
     int tot_nodes = h->tot_nodes, log_len = h->log_len, mt_pos = h->mt_pos, n_expanded = h->n_expanded, err = h->err;
     const int len = h->path_len;
@@ -262,6 +267,7 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
     const float *vv = f_vsval(L, tb);
     float *reward = f_reward(L, tb), *wsum = f_wsum(L, tb), *wtot = f_wtot(L, tb);
 
+    MAZ_TS(L, tree, lane, 1);
     // ---- round trip 2: issue everything that depends only on the header -------------------------------------
     const bool fast = len < 32;                       // path fits one lane per node (else: per-node loads below)
     int my_slot = 0;
@@ -281,6 +287,7 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
         for (int t = lane; t < n_draw; t += 32) sc.draws[t] = mt_temper(mt[mt_pos + t]);
         mt_pos += n_draw;
     }
+    const float my_lp = (fast && lane <= len) ? lam_pow[lane] : 0.f;   // lam_pow[depth], depth = lane
     // ---- round trip 3: per-path-node fields, lane i <-> path[i] ------------------------------------------------
     const int leaf = fast ? __shfl_sync(MAZ_FULL, my_slot, len) : (int)path[len];
     float my_rew = 0.f, my_ws = 0.f, my_wt = 0.f, my_ppv = 0.f;
@@ -297,12 +304,14 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
         if (fast && lane >= 1 && lane <= len) my_ppv = f_pred_value(L, tb)[prev];   // parent's pred_value
     }
 
+    MAZ_TS(L, tree, lane, 2);
     // PDL: everything above only touched this tree's own state (written by the previous tree kernel, long
     // complete); the network outputs of THIS simulation are produced by the kernel we may be overlapping with.
     griddep_wait();
     const float reward_in = __ldcg(reward_ptr), value = __ldcg(value_ptr);   // L2 loads, see expand_node
     expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, reward_in, value, probs, beta, K, 0.0f, nullptr, sc,
-                lane, draws_pre);
+                lane, draws_pre, tree);
+    MAZ_TS(L, tree, lane, 3);
 
     // ---- back_propagate (cnode.cpp:415-450) -----------------------------------------------------------------------
     float *qd = f_qdelta(L, tb);                      // q-delta of the e-th expanded node (the CMinMaxStats entries)
@@ -334,7 +343,8 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
 #pragma unroll
         for (int c = 0; c < kLogRegs; ++c) vs_scan_entry(r, tag, lk[c], lv[c], c * 32 + lane);
         for (int e = kLogRegs * 32 + lane; e < log_len0; e += 32) vs_scan_entry(r, tag, vk[e], vv[e], e);
-        vs_apply(L, tb, log_len, err, ws, wt, tag, len - i, G, lam_pow, lane, r);
+        const float lp = fast ? __shfl_sync(MAZ_FULL, my_lp, len - i) : lam_pow[len - i];
+        vs_apply(L, tb, log_len, err, ws, wt, tag, lp, G, lane, r);
         if (lane == 0) {
             f_visit(L, tb)[slot] = vis + 1;
             wsum[slot] = ws;
@@ -344,6 +354,7 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
         G = __fadd_rn(rew, __fmul_rn(discount, G));
     }
     __syncwarp();
+    MAZ_TS(L, tree, lane, 4);
     // CMinMaxStats min / max = reduction over the q-deltas of all visited (= expanded) non-root nodes
     uint32_t lo = 0xffffffffu, hi = 0u;
     for (int e = 1 + lane; e < n_expanded; e += 32) {
@@ -364,6 +375,7 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
         h->err = err;
         if (err) *g_err = err;
     }
+    MAZ_TS(L, tree, lane, 5);
 }
 
 __global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restrict__ lam_pow, int hidx, float discount,
@@ -395,9 +407,10 @@ __global__ void k_expand_backup_select(TreeLayout L, char *arena, const float *_
     const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
     const size_t NA = (size_t)L.N * L.A;
     expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
-                         beta + tree * NA, sc, lane, g_err);
+                         beta + tree * NA, sc, lane, g_err, tree);
     __syncwarp();
     select_path_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
+    MAZ_TS(L, tree, lane, 6);
 }
 
 // ---- readouts (cnode.cpp:69-171, 471-530, 672-781) ------------------------------------------------------

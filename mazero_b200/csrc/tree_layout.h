@@ -44,6 +44,9 @@ struct TreeLayout {
     int L;        // value-log capacity = 1 + S*(S+3)/2 + slack (worst case: one chain)
     float delta_lb, one_minus_rho, lam;
     unsigned long long slab_bytes;
+    long long *dbg_clock;   // profiling only (NULL): SM-cycle timestamps of tree 0's phases, 64 entries
+    const float *pbc_table; // pb_c[n][visit] = (float)((double)logterm[n] * (sqrt((double)n) / (double)(visit + 1))), host-built
+    int pbc_dim;            // table is pbc_dim x pbc_dim (0: compute on the device with fp64)
     // byte offsets inside a slab (all multiples of 128)
     unsigned off_mt, off_prior, off_pred_prob, off_beta, off_beta_hat, off_reward, off_pred_value, off_wsum, off_wtot,
         off_qdelta, off_visit, off_nchild, off_cbase, off_hidx, off_eid, off_actions, off_expslot, off_path, off_vskey, off_vsval;

@@ -47,3 +47,17 @@ print("k_select us:", [round(e[0].elapsed_time(e[1]) * 1e3, 1) for e in evs])
 print("k_expand_backup us:", [round(e[1].elapsed_time(e[2]) * 1e3, 1) for e in evs])
 tot, sl, s1, s2 = t.stats()
 print("mean depth", s1 / (B * sims), "nodes/tree", tot.mean())
+
+if os.environ.get("STAGE_CLOCKS"):
+    from mazero_b200._lib import lib, check
+    import ctypes as C
+    dbg = torch.zeros(64, dtype=torch.int64, device=dev)
+    check(lib.maz_tree_set_debug_clock(t._h, C.c_void_p(dbg.data_ptr())))
+    t.expansion_backup_selection_device(sims + 1 if sims + 1 <= S else S, 0.99, K, rews[sims], vals[sims], probs[sims], probs[sims],
+                                        19652.0, 1.25, ix, iy, act)
+    t.check()
+    c = dbg.cpu().numpy()
+    names = {0: "start", 1: "hdr loaded", 11: "beta/probs staged", 12: "cdf built", 13: "sampled", 14: "dedup", 15: "children written",
+             2: "prefetch issued", 3: "expanded", 4: "backup done", 5: "minmax+hdr written", 6: "select done"}
+    order = [0, 1, 2, 11, 12, 13, 14, 15, 3, 4, 5, 6]
+    print("fused tree kernel, tree 0, cycles since start:", {names[k]: int(c[k] - c[0]) for k in order})
