@@ -327,9 +327,10 @@ __device__ __forceinline__ void attention_head_small(uint32_t trow, uint32_t sb,
     store_cols(tile, row, hh * HD, H, o);
 }
 
-__device__ __noinline__ void epi_attention(uint32_t trow, uint32_t sb, int N, int root_lane0, uint32_t tile)
+__device__ __noinline__ void epi_attention(uint32_t trow, uint32_t sb, int N, int root_lane0, uint32_t tile, uint32_t scratch)
 {
     const Thr t;
+    const uint32_t kv = scratch + (uint32_t)(t.part * 4 + t.quad) * 2048u;   // this warp's 32 x (K16 | V16) bf16 rows
 #pragma unroll 1
     for (int hh = t.part * HPP; hh < (t.part + 1) * HPP; ++hh) {
         if (N <= 4) {   // warp-uniform
@@ -341,33 +342,61 @@ __device__ __noinline__ void epi_attention(uint32_t trow, uint32_t sb, int N, in
             }
             continue;
         }
-        float q[16], k[16], v[16], o[16];
-        tmem_ld16(trow + TM_Q + hh * HD, q);
-        tmem_ld16(trow + TM_K + hh * HD, k);
-        tmem_ld16(trow + TM_V + hh * HD, v);
-        add_svec(q, sb + 4 * (hh * HD));
-        add_svec(k, sb + 4 * (H + hh * HD));
-        add_svec(v, sb + 4 * (2 * H + hh * HD));
+        // Larger teams: K and V of the warp's 32 rows go through shared memory as bf16 (2 KB per warp, in the operand
+        // tile that the QKV GEMM has just finished reading), so each key costs 4 broadcast LDS.128 instead of 32 warp
+        // shuffles (the shuffle crossbar bounded this loop: 27 keys x 32 shuffles x 2 heads per warp and layer at N = 27).
+        float q[16], o[16];
+        {
+            float k[16], v[16];
+            tmem_ld16(trow + TM_Q + hh * HD, q);
+            tmem_ld16(trow + TM_K + hh * HD, k);
+            tmem_ld16(trow + TM_V + hh * HD, v);
+            add_svec(q, sb + 4 * (hh * HD));
+            add_svec(k, sb + 4 * (H + hh * HD));
+            add_svec(v, sb + 4 * (2 * H + hh * HD));
+            const uint32_t mine = kv + (uint32_t)t.lane * 64u;
+            uint4 a, b2;
+            a.x = pack2(k[0], k[1]); a.y = pack2(k[2], k[3]); a.z = pack2(k[4], k[5]); a.w = pack2(k[6], k[7]);
+            b2.x = pack2(k[8], k[9]); b2.y = pack2(k[10], k[11]); b2.z = pack2(k[12], k[13]); b2.w = pack2(k[14], k[15]);
+            sts4(mine, a);
+            sts4(mine + 16, b2);
+            a.x = pack2(v[0], v[1]); a.y = pack2(v[2], v[3]); a.z = pack2(v[4], v[5]); a.w = pack2(v[6], v[7]);
+            b2.x = pack2(v[8], v[9]); b2.y = pack2(v[10], v[11]); b2.z = pack2(v[12], v[13]); b2.w = pack2(v[14], v[15]);
+            sts4(mine + 32, a);
+            sts4(mine + 48, b2);
+        }
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 16; ++i) { q[i] *= 0.25f; o[i] = 0.f; }   // 1/sqrt(head_dim)
         float m = -INFINITY, lsum = 0.f;
 #pragma unroll 1
         for (int j = 0; j < N; ++j) {
-            const int src = root_lane0 + j;
+            const uint32_t rowp = kv + (uint32_t)(root_lane0 + j) * 64u;
+            uint32_t w[16];
+            lds4u(rowp, w[0], w[1], w[2], w[3]);
+            lds4u(rowp + 16, w[4], w[5], w[6], w[7]);
+            lds4u(rowp + 32, w[8], w[9], w[10], w[11]);
+            lds4u(rowp + 48, w[12], w[13], w[14], w[15]);
             float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) s += q[i] * __shfl_sync(0xffffffffu, k[i], src);
+            for (int i = 0; i < 8; ++i) {   // bf16 pair -> two fp32: low half << 16, high half masked
+                s += q[2 * i] * __uint_as_float(w[i] << 16) + q[2 * i + 1] * __uint_as_float(w[i] & 0xffff0000u);
+            }
             const float mn = fmaxf(m, s);
             const float corr = __expf(m - mn), p = __expf(s - mn);
             lsum = lsum * corr + p;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = o[i] * corr + p * __shfl_sync(0xffffffffu, v[i], src);
+            for (int i = 0; i < 8; ++i) {
+                o[2 * i] = o[2 * i] * corr + p * __uint_as_float(w[8 + i] << 16);
+                o[2 * i + 1] = o[2 * i + 1] * corr + p * __uint_as_float(w[8 + i] & 0xffff0000u);
+            }
             m = mn;
         }
         const float inv = 1.f / lsum;
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] *= inv;
         store_cols(tile, t.row, hh * HD, H, o);
+        __syncwarp();   // every lane is done with this head's K / V before the next head overwrites them
     }
 }
 
@@ -759,7 +788,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
         for (int l = 0; l < NLAYER; ++l) {
             const uint32_t lv = aP + 4 * (d.o_layer + l * 1280);   // bq bk bv bo g1 be1 b1 b2 g2 be2
             HANDOFF(3);
-            if (do_epi) epi_attention(trow, lv, N, root_lane0, aT);
+            if (do_epi) epi_attention(trow, lv, N, root_lane0, aT, aX);   // sX is free: the QKV GEMM is done with it
             HANDOFF(1);
             if (do_epi) epi_ln128(trow, TM_X, lv + 4 * 384, lv + 4 * 512, lv + 4 * 640, 0, 1, aX, aRed);     // norm1
             HANDOFF(1);

@@ -195,6 +195,10 @@ __device__ __forceinline__ float4 lds4(uint32_t saddr)
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ void lds4u(uint32_t saddr, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d)
+{
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr) : "memory");
+}
 __device__ __forceinline__ float lds1(uint32_t saddr)
 {
     float v;
