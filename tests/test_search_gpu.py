@@ -127,3 +127,51 @@ def test_device_path_accepts_reference_style_module(built_lib):
     assert all(o.sampled_actions[b].shape[1] == 1 for b in range(B))
     with pytest.raises(NotImplementedError):
         mcts.batch_search(model, out0, 0, None, N, None, torch.device("cuda:0"), sampled_actions_res=(None, None))
+
+
+class _RefStyleModel:
+    """Reference-style interface (numpy reward / value / logits, torch hidden) around the CPU fp32 network."""
+
+    def __init__(self, net):
+        self.net = net
+
+    def eval(self):
+        return self
+
+    def prediction(self, hidden):
+        pol, vlog = self.net.prediction(hidden)
+        return pol.detach().numpy(), vlog.detach().numpy()
+
+    def recurrent_inference(self, hidden, action):
+        from oracle.search_oracle import NetworkOutput
+
+        nxt, r, v, pl = self.net.recurrent_inference(hidden, action)
+        return NetworkOutput(nxt, r.numpy(), v.numpy(), pl.numpy())
+
+
+@pytest.mark.parametrize("cur", [None, 0, 2])
+def test_step_path_equals_restated_reference_driver(built_lib, oracle_built, cur):
+    """Whole `batch_search` of the product (CUDA tree, reference loop, real fp32 network on the CPU) against the restated
+    reference driver over the CPU oracle tree: identical network outputs by construction, so EVERY field of SearchOutput
+    must be bit-identical (root preparation, RNG consumption order, legal mask, noise, sequential-agent joint actions)."""
+    from mazero_b200.mcts_sampled import SampledMCTS
+    from oracle.search_oracle import reference_batch_search
+
+    N, A, B, K, S = 3, 9, 20, 10, 15
+    cfg = MockConfig(N, A, S, K)
+    net = smac_model(N, A, h=32)
+    model = _RefStyleModel(net)
+    out0 = root_output(net, B)
+    legal = (np.random.RandomState(6).rand(B, N, A) < 0.7).astype(np.float32)
+    legal[..., 1] = 1
+    factor = np.random.RandomState(5).randint(0, A, size=(B, N)).astype(np.int32)
+    ours = SampledMCTS(cfg, np.random.RandomState(11)).batch_search(model, out0, cur, factor, N, legal.copy(), torch.device("cpu"),
+                                                                     add_noise=True, sampled_tau=1.0)
+    ref = reference_batch_search(cfg, np.random.RandomState(11), model, out0, cur, factor, N, legal.copy(), torch.device("cpu"),
+                                 add_noise=True, sampled_tau=1.0, tree_kind="port")
+    for f in ours._fields:
+        x, y = getattr(ours, f), getattr(ref, f)
+        if isinstance(y, np.ndarray):
+            assert np.array_equal(x, y), f
+        else:
+            assert len(x) == len(y) and all(np.array_equal(a, b) for a, b in zip(x, y)), f
