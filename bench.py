@@ -337,7 +337,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp) and args.workload == "3m" and args.mode == "joint":
         traffic = json.load(open(tp))
-    tree_roof = {"bound": "hbm", "kernel": "k_expand_backup_select", "achieved": bytes_tree / (ms_tree * 1e-3) / 1e9,
+    tree_roof = {"bound": "hbm", "kernel": "k_expand_backup_select2", "achieved": bytes_tree / (ms_tree * 1e-3) / 1e9,
                  "peak": hbm_peak, "unit": "GB/s", "frac": bytes_tree / (ms_tree * 1e-3) / 1e9 / hbm_peak,
                  "traffic": (traffic.get("k_expand_backup:3m:joint", 0) + traffic.get("k_select:3m:joint", 0)) or None,
                  "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_tree, "launch_ms": ms_tree}

@@ -202,7 +202,8 @@ int maz_tree_create_ex(maz_tree **out, int B, int N, int A, int K, int S, float 
     if (dyn > 48 * 1024) {
         if ((e = cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess ||
             (e = cudaFuncSetAttribute(k_expand_backup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess ||
-            (e = cudaFuncSetAttribute(k_expand_backup_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess)
+            (e = cudaFuncSetAttribute(k_expand_backup_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess ||
+            (e = cudaFuncSetAttribute(k_expand_backup_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess)
             return fail(MAZ_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     }
     if ((rc = upload_lam_pow(t)) != MAZ_OK) { std::string m = g_last_error; return fail(rc, m); }
@@ -366,8 +367,9 @@ int maz_tree_expansion_backup_selection_dev(maz_tree *t, int hidx, float discoun
     DeviceGuard g(t->device);
     // launched as a programmatic dependent of the inference kernel: the tree-state prefetch overlaps its tail
     cudaLaunchConfig_t cfg = {};
+    // two warps per tree (expansion || backup): wpb trees per block -> 64 * wpb threads
     cfg.gridDim = tree_grid(t);
-    cfg.blockDim = tree_block(t);
+    cfg.blockDim = dim3(64u * t->wpb);
     cfg.dynamicSmemBytes = t->scratch_per_warp * t->wpb;
     cfg.stream = t->stream;
     cudaLaunchAttribute attr[1];
@@ -377,7 +379,7 @@ int maz_tree_expansion_backup_selection_dev(maz_tree *t, int hidx, float discoun
     cfg.numAttrs = (maz::pdl_mask() & 2) ? 1 : 0;
     const float *lam = t->d_lam_pow, *lt = t->d_logterm;
     const double *sq = t->d_sqrtn;
-    CU_TRY(cudaLaunchKernelEx(&cfg, k_expand_backup_select, t->L, t->arena, lam, hidx, discount, K, rewards, values, probs, beta,
+    CU_TRY(cudaLaunchKernelEx(&cfg, k_expand_backup_select2, t->L, t->arena, lam, hidx, discount, K, rewards, values, probs, beta,
                               lt, sq, t->table_len, idx_x, idx_y, act, t->d_err));
     return MAZ_OK;
 }

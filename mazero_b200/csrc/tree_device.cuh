@@ -204,7 +204,8 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
                                            int &err, int slot, int hidx, float reward, float value,
                                            const float *__restrict__ probs, const float *__restrict__ beta,
                                            int K, float eps, const float *__restrict__ noises,
-                                           const ExpandScratch &sc, int lane, bool draws_prefetched = false, int dbg_tree = -1)
+                                           const ExpandScratch &sc, int lane, bool draws_prefetched = false, int dbg_tree = -1,
+                                           bool init_stats = true)
 {
     const int N = L.N, A = L.A, NA = N * A;
 
@@ -353,8 +354,10 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
         f_pred_value(L, tb)[slot] = value;
         f_nchild(L, tb)[slot] = (uint16_t)C;
         f_cbase(L, tb)[slot] = (uint16_t)base;
-        f_wsum(L, tb)[slot] = 0.0f;
-        f_wtot(L, tb)[slot] = 0.0f;
+        if (init_stats) {   // (two-warp kernel: the backup warp owns the leaf's statistics)
+            f_wsum(L, tb)[slot] = 0.0f;
+            f_wtot(L, tb)[slot] = 0.0f;
+        }
         f_expslot(L, tb)[n_expanded] = (uint16_t)slot;
         f_eid(L, tb)[slot] = (uint16_t)n_expanded;   // expansion order: index of this node's q-delta entry
     }

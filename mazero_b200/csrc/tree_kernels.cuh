@@ -413,6 +413,145 @@ __global__ void k_expand_backup_select(TreeLayout L, char *arena, const float *_
     MAZ_TS(L, tree, lane, 6);
 }
 
+// ---- the same step with TWO warps per tree: expansion and back-propagation touch disjoint state (the expansion
+// samples and creates children: RNG, node pool; the backup walks the path: value log, visit counts, q-deltas), so they
+// run concurrently; the next selection needs both and follows a block barrier.  Same arithmetic, same results; the
+// tree step is a chain of dependent instructions on a mostly idle SM, so the second warp is free. -----------------------
+__global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *__restrict__ lam_pow, int hidx, float discount,
+                                        int K, const float *__restrict__ rewards, const float *__restrict__ values,
+                                        const float *__restrict__ probs, const float *__restrict__ beta,
+                                        const float *__restrict__ logterm, const double *__restrict__ sqrtn, int table_len,
+                                        int *__restrict__ idx_x, int *__restrict__ idx_y, int *__restrict__ act_out, int *g_err)
+{
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = warp >> 1, role = warp & 1;              // role 0: expansion (+ selection), role 1: backup
+    const int tree = blockIdx.x * (blockDim.x >> 6) + pair;
+    const bool active = tree < L.B;
+    char *tb = arena + (size_t)(active ? tree : 0) * L.slab_bytes;
+    TreeHdr *h = f_hdr(tb);
+    const size_t NA = (size_t)L.N * L.A;
+    griddep_launch();
+    // both warps read the header BEFORE either of them may write it
+    const int tot_nodes0 = h->tot_nodes, log_len0 = h->log_len, mt_pos0 = h->mt_pos, n_exp0 = h->n_expanded, err0 = h->err;
+    const int len = h->path_len;
+    __syncthreads();
+    if (active && role == 0) {
+        // ---------------- expansion (cnode.cpp:224-295) ----------------
+        const ExpandScratch sc = carve_scratch(smem + (size_t)pair * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+        int tot_nodes = tot_nodes0, n_expanded = n_exp0, mt_pos = mt_pos0, err = err0;
+        const int leaf = f_path(L, tb)[len];
+        const int n_draw = (L.A >= 2) ? 2 * K * L.N : 0;
+        const bool draws_pre = n_draw > 0 && n_draw <= kMtChunk && mt_pos + n_draw <= kMtN;
+        if (draws_pre) {
+            const uint32_t *mt = f_mt(L, tb);
+            for (int t = lane; t < n_draw; t += 32) sc.draws[t] = mt_temper(mt[mt_pos + t]);
+            mt_pos += n_draw;
+        }
+        griddep_wait();
+        expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, __ldcg(rewards + tree), __ldcg(values + tree),
+                    probs + tree * NA, beta + tree * NA, K, 0.0f, nullptr, sc, lane, draws_pre, -1, /*init_stats=*/false);
+        if (lane == 0) {
+            h->tot_nodes = tot_nodes;
+            h->mt_pos = mt_pos;
+            h->n_expanded = n_expanded;
+            h->err = err;
+            if (err) *g_err = err;
+        }
+    } else if (active) {
+        // ---------------- back_propagate (cnode.cpp:415-450) ----------------
+        int log_len = log_len0, err = 0;
+        const uint16_t *path = f_path(L, tb);
+        const uint32_t *vk = f_vskey(L, tb);
+        const float *vv = f_vsval(L, tb);
+        float *reward = f_reward(L, tb), *wsum = f_wsum(L, tb), *wtot = f_wtot(L, tb);
+        const bool fast = len < 32;
+        int my_slot = 0;
+        if (fast && lane <= len) my_slot = path[lane];
+        uint32_t lk[kLogRegs];
+        float lv[kLogRegs];
+#pragma unroll
+        for (int c = 0; c < kLogRegs; ++c) {
+            const int e = c * 32 + lane;
+            lk[c] = (e < log_len0) ? vk[e] : 0xffffffffu;
+            lv[c] = (e < log_len0) ? vv[e] : 0.0f;
+        }
+        const float my_lp = (fast && lane <= len) ? lam_pow[lane] : 0.f;
+        float my_rew = 0.f, my_ws = 0.f, my_wt = 0.f, my_ppv = 0.f;
+        int my_vis = 0, my_eid = 0;
+        if (fast && lane < len) {
+            my_rew = reward[my_slot];
+            my_ws = wsum[my_slot];
+            my_wt = wtot[my_slot];
+            my_vis = f_visit(L, tb)[my_slot];
+            my_eid = f_eid(L, tb)[my_slot];
+        }
+        {
+            const int prev = __shfl_up_sync(MAZ_FULL, my_slot, 1);
+            if (fast && lane >= 1 && lane <= len) my_ppv = f_pred_value(L, tb)[prev];
+        }
+        griddep_wait();
+        const float reward_in = __ldcg(rewards + tree), value = __ldcg(values + tree);
+        float *qd = f_qdelta(L, tb);
+        float G = value;
+        for (int i = len; i >= 0; --i) {
+            int slot, vis, nh;
+            float rew, ws, wt, ppv;
+            if (fast) {
+                slot = __shfl_sync(MAZ_FULL, my_slot, i);
+                rew = __shfl_sync(MAZ_FULL, my_rew, i);
+                ws = __shfl_sync(MAZ_FULL, my_ws, i);
+                wt = __shfl_sync(MAZ_FULL, my_wt, i);
+                vis = __shfl_sync(MAZ_FULL, my_vis, i);
+                nh = __shfl_sync(MAZ_FULL, my_eid, i);
+                ppv = __shfl_sync(MAZ_FULL, my_ppv, i);
+            } else {
+                slot = path[i];
+                rew = reward[slot]; ws = wsum[slot]; wt = wtot[slot];
+                vis = f_visit(L, tb)[slot];
+                nh = f_eid(L, tb)[slot];
+                ppv = (i > 0) ? f_pred_value(L, tb)[path[i - 1]] : 0.f;
+            }
+            if (i == len) { rew = reward_in; ws = 0.f; wt = 0.f; vis = 0; nh = n_exp0; }   // the leaf being expanded
+            const uint32_t tag = vs_tag(slot, len - i);
+            VsScan r;
+            vs_scan_init(r);
+#pragma unroll
+            for (int c = 0; c < kLogRegs; ++c) vs_scan_entry(r, tag, lk[c], lv[c], c * 32 + lane);
+            for (int e = kLogRegs * 32 + lane; e < log_len0; e += 32) vs_scan_entry(r, tag, vk[e], vv[e], e);
+            const float lp = fast ? __shfl_sync(MAZ_FULL, my_lp, len - i) : lam_pow[len - i];
+            vs_apply(L, tb, log_len, err, ws, wt, tag, lp, G, lane, r);
+            if (lane == 0) {
+                f_visit(L, tb)[slot] = vis + 1;
+                wsum[slot] = ws;
+                wtot[slot] = wt;
+                if (i != 0) qd[nh] = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), ppv);
+            }
+            G = __fadd_rn(rew, __fmul_rn(discount, G));
+        }
+        __syncwarp();
+        const int n_exp1 = n_exp0 + 1;
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        for (int e = 1 + lane; e < n_exp1; e += 32) {
+            const uint32_t o = f2ord(qd[e]);
+            lo = min(lo, o);
+            hi = max(hi, o);
+        }
+        lo = __reduce_min_sync(MAZ_FULL, lo);
+        hi = __reduce_max_sync(MAZ_FULL, hi);
+        if (lane == 0) {
+            h->log_len = log_len;
+            h->mm_cnt = n_exp1 - 1;
+            h->mm_min = ord2f(lo);
+            h->mm_max = ord2f(hi);
+            if (err) *g_err = err;
+        }
+    }
+    __syncthreads();   // expansion and backup of every tree of the block are complete and visible
+    if (active && role == 0)
+        select_path_device(L, tb, h, logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
+}
+
 // ---- readouts (cnode.cpp:69-171, 471-530, 672-781) ------------------------------------------------------
 struct ReadoutPtrs {
     float *values;
