@@ -79,7 +79,9 @@ def _output_from_readout(r):
 
 
 class _DevicePlan:
-    """Static buffers + the captured CUDA graph of S simulations for one problem shape."""
+    """Static buffers + the captured CUDA graphs of S simulations for one problem shape.  The sequential-agent turns
+    (current_agent_idx = 0..N-1) share ONE plan -- tree arena, hidden-state pool and staging buffers are by far the
+    largest allocations -- and differ only in their captured graph (`graphs[cur]`)."""
 
     def __init__(self, inf: SmacInference, B, K, S, cur, cfg, tau, use_graph=True):
         self.inf, self.B, self.K, self.S, self.cur, self.tau = inf, B, K, S, cur, float(tau)
@@ -106,7 +108,7 @@ class _DevicePlan:
         # per-simulation network outputs (fused path writes them in place)
         self.sim_r, self.sim_v = z(B), z(B)
         self.sim_p, self.sim_b = z(B, self.Nt, self.A), z(B, self.Nt, self.A)
-        self.graph = None
+        self.graphs = {}   # current_agent_idx (or None) -> captured CUDA graph
         self.use_graph = use_graph
         self.record = None  # when a list: per-simulation injected arrays are appended (parity replay tests)
         # all readouts live in ONE device buffer mirrored by ONE pinned host buffer: one D2H copy per search
@@ -180,9 +182,16 @@ class _DevicePlan:
         for s in range(self.S):
             self._simulate(s, select_first=(s == 0 or not fuse), select_next=(fuse and s + 1 < self.S))
 
+    @property
+    def graph(self):
+        return self.graphs.get(self.cur)
+
     def run(self, seed, cfg, noise_eps, root_hidden, rewards, values, probs, beta, noises, root_greedy, factor,
-            root_index_offset=0):
+            root_index_offset=0, cur="same"):
         """root_* host numpy (pinned or not) or device tensors; returns the padded readout dict (host numpy)."""
+        if cur != "same":
+            assert (cur is None) == (self.cur is None), "a plan is either joint or sequential"
+            self.cur = cur
         stream = torch.cuda.current_stream(self.dev)
         self.tree.set_stream(stream.cuda_stream)
         cp = lambda dst, src: dst.copy_(src if torch.is_tensor(src) else torch.from_numpy(np.ascontiguousarray(src)), non_blocking=True)
@@ -200,11 +209,11 @@ class _DevicePlan:
             self.tree.prepare(self.root_r, self.root_v, self.root_p, self.root_b, self.K, float(noise_eps), self.root_n)
 
         if self.use_graph and self.record is None:
-            if self.graph is None:
+            if self.cur not in self.graphs:
                 prepare()          # the capture warm-up runs one real simulation: it needs valid roots
                 self._capture()
             prepare()
-            self.graph.replay()
+            self.graphs[self.cur].replay()
         else:
             prepare()
             self._loop()
@@ -228,7 +237,7 @@ class _DevicePlan:
             self.tree.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
             self._loop()
         self.tree.set_stream(cur.cuda_stream)
-        self.graph = g
+        self.graphs[self.cur] = g
 
 
 class SampledMCTS(object):
@@ -341,14 +350,14 @@ class SampledMCTS(object):
 
         inf = self._device_inference(model, device)
         if inf is not None:
-            key = (id(inf), B, K, cfg.num_simulations, current_agent_idx, float(sampled_tau))
+            key = (id(inf), B, K, cfg.num_simulations, joint, float(sampled_tau))   # all sequential turns share a plan
             plan = self._plans.get(key)
             if plan is None:
                 plan = _DevicePlan(inf, B, K, cfg.num_simulations, current_agent_idx, cfg, sampled_tau, self.use_cuda_graph)
                 self._plans[key] = plan
             root_greedy = np.argmax(all_logits.reshape(B, true_num_agents, A), axis=-1).astype(np.int32)
             r = plan.run(int(seed), cfg, noise_epsilon, network_output.hidden_state, batch_rewards, batch_values, probs, beta,
-                         noises, root_greedy, factor, root_index_offset)
+                         noises, root_greedy, factor, root_index_offset, cur=current_agent_idx)
             return _output_from_readout(r)
         return self._search_step_path(model, network_output, current_agent_idx, factor, true_num_agents, device, sampled_tau,
                                       seed, noise_epsilon, batch_rewards, batch_values, probs, beta, noises, root_index_offset)

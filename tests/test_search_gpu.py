@@ -175,3 +175,32 @@ def test_step_path_equals_restated_reference_driver(built_lib, oracle_built, cur
             assert np.array_equal(x, y), f
         else:
             assert len(x) == len(y) and all(np.array_equal(a, b) for a, b in zip(x, y)), f
+
+
+def test_sequential_turns_share_one_plan_without_leaking_state(built_lib):
+    """The per-agent loop of the workers (selfplay_worker.py:196-211) calls batch_search N times on one SampledMCTS:
+    one device plan (arena, pool) serves all turns, one captured graph per turn, and a turn's result does not depend
+    on the turns run before it."""
+    from mazero_b200.inference import SmacInference
+    from mazero_b200.mcts_sampled import SampledMCTS
+
+    N, A, B, K, S = 3, 9, 24, 10, 12
+    cfg = MockConfig(N, A, S, K)
+    model = smac_model(N, A)
+    inf = SmacInference.from_model(model, device="cuda:0", mode="bf16")
+    out0 = root_output(model, B)
+    out0 = out0._replace(hidden_state=out0.hidden_state.cuda())
+    factor = np.random.RandomState(5).randint(0, A, size=(B, N)).astype(np.int32)
+    shared = SampledMCTS(cfg, np.random.RandomState(0))
+    looped = []
+    for cur in (0, 1, 2, 1):
+        shared.np_random = np.random.RandomState(100 + cur)
+        looped.append(shared.batch_search(inf, out0, cur, factor, N, None, "cuda:0", add_noise=True))
+    assert len(shared._plans) == 1
+    plan = next(iter(shared._plans.values()))
+    assert sorted(plan.graphs) == [0, 1, 2]
+    fresh = SampledMCTS(cfg, np.random.RandomState(101)).batch_search(inf, out0, 1, factor, N, None, "cuda:0", add_noise=True)
+    for o in (looped[1], looped[3]):
+        assert np.array_equal(o.value, fresh.value)
+        assert np.array_equal(o.marginal_visit_count, fresh.marginal_visit_count)
+        assert o.sampled_qvalues == fresh.sampled_qvalues
