@@ -229,7 +229,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
     gather = None
     if world > 1:   # one exchange per search: root values + visit counts to every rank (learner = rank 0)
-        gather = [torch.empty_like(plan.out_flat) for _ in range(world)]
+        gather = torch.empty(world * plan.out_flat.numel(), dtype=plan.out_flat.dtype, device=dev)
 
     def dev_step(seed):
         plan.tree.reset(seed, cfg.tree_value_stat_delta_lb, cfg.mcts_rho, cfg.mcts_lambda, root_off)
@@ -240,7 +240,7 @@ def run_ours(args):
             plan._loop()
         plan.tree.readout_device(cfg.discount, plan.out)
         if gather is not None:
-            dist.all_gather(gather, plan.out_flat)
+            dist.all_gather_into_tensor(gather, plan.out_flat)   # ONE collective per search (NCCL over NVLink)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
