@@ -50,6 +50,44 @@ typedef struct maz_infer_desc {
 /* replaces model.recurrent_inference + the driver's softmax/beta (mcts_sampled.py:150-161): one kernel launch */
 int maz_infer_recurrent(const maz_infer_desc *desc, void *cuda_stream);
 
+/* ---- MLP-family network (the reference's matrix-game MAMuZeroNet) --------------------------------------------
+ * Replaces, for the search only, config/matrix/model.py:358-368 `recurrent_inference` (= `dynamics` :334-343 /
+ * DynamicsNetwork.forward :118-126 + PredictionNetwork.forward :163-166) and the driver's softmax / beta
+ * (mcts_sampled.py:158-161).  fp32 SIMT kernel, one CTA per root; device pointers; asynchronous on the stream.
+ * A layer computes y = W x + b followed by nothing (MAZ_MLP_LINEAR), ReLU then LayerNorm (MAZ_MLP_RELU_LN, the
+ * matrix mlp() order, config/matrix/model.py:44-46) or LayerNorm then ReLU (MAZ_MLP_LN_RELU, the SMAC order).
+ * `wt` is the weight TRANSPOSED to [in][out] (row-major). */
+#define MAZ_MLP_MAXLAYERS 6
+#define MAZ_MLP_MAXWIDTH 640
+enum { MAZ_MLP_LINEAR = 0, MAZ_MLP_RELU_LN = 1, MAZ_MLP_LN_RELU = 2 };
+typedef struct maz_mlp_layer {
+    const float *wt, *b, *ln_w, *ln_b;   /* ln_* NULL for MAZ_MLP_LINEAR */
+    int in, out, kind;
+} maz_mlp_layer;
+typedef struct maz_mlp_net {
+    int n;
+    maz_mlp_layer l[MAZ_MLP_MAXLAYERS];
+} maz_mlp_net;
+typedef struct maz_mlp_desc {
+    int B, N, A, H;              /* roots, agents, actions per agent, hidden size per agent */
+    int Nt, cur;                 /* agents in the tree (N joint / 1 sequential), sequential agent index or -1 */
+    float inv_tau;               /* 1 / sampled_tau */
+    const float *pool;           /* hidden-state pool: row (idx*B + b), N*H floats */
+    const int *idx_x;            /* (B,) or NULL (= 0) */
+    const int *actions;          /* (B,N) joint action */
+    float *next_hidden;          /* (B, N*H) */
+    float *reward, *value;       /* (B,) scalars after the inverse support transform */
+    float *probs, *beta;         /* (B,Nt,A) */
+    int *greedy;                 /* (B,N) argmax_a of the policy logits, or NULL */
+    float *logits_out;           /* (B,N,A) raw policy logits, or NULL */
+    maz_mlp_net dyn, rew, val, pol;   /* fc_dynamic (N*H+N*A -> N*H), fc_reward (N*H+N*A -> support),
+                                         fc_value (N*H -> support), fc_policy (H -> A, applied per agent) */
+    int reward_support_min, reward_support_size;   /* size 1: scalar head, no transform (use_vectorization=False) */
+    int value_support_min, value_support_size;
+} maz_mlp_desc;
+
+int maz_mlp_recurrent(const maz_mlp_desc *desc, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,7 @@ SIGNATURES = {
     # include/maz_infer.h
     "maz_dbg_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "maz_infer_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "maz_mlp_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 if not os.path.exists(LIB_PATH):

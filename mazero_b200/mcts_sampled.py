@@ -22,6 +22,8 @@ import torch
 
 from . import cytree
 from .inference import SmacInference
+from .inference_mlp import MlpInference
+from . import inference_mlp
 
 
 class SearchOutput(NamedTuple):  # mcts_sampled.py:12-26
@@ -254,7 +256,7 @@ class SampledMCTS(object):
 
     # ---- model adaptation ---------------------------------------------------------------------------------
     def _device_inference(self, model, device) -> Optional[SmacInference]:
-        if isinstance(model, SmacInference):
+        if isinstance(model, (SmacInference, MlpInference)):
             return model
         if not isinstance(model, torch.nn.Module):
             return None
@@ -262,15 +264,21 @@ class SampledMCTS(object):
             sd = model.state_dict()
         except Exception:
             return None
-        if "dynamics_network.attention_stack.0.weight" not in sd or "prediction_network.fc_policy.0.weight" not in sd:
+        smac = "dynamics_network.attention_stack.0.weight" in sd and "prediction_network.fc_policy.0.weight" in sd
+        mlp = not smac and inference_mlp.supported(sd)     # the matrix-game family (config/matrix/model.py)
+        if not smac and not mlp:
             return None
-        dev = torch.device(device) if device is not None else sd["dynamics_network.attention_stack.0.weight"].device
+        dev = torch.device(device) if device is not None else sd["prediction_network.fc_policy.0.weight"].device
         if dev.type != "cuda":
             return None
         key = (id(model), str(dev))
         inf = self._inference.get(key)
         version = sum(int(getattr(p, "_version", 0)) for p in sd.values())
-        if inf is None:
+        if inf is None and mlp:
+            inf = MlpInference.from_model(model, device=dev, mode="torch" if self.inference_mode == "torch" else "fp32")
+            inf._src_version = version
+            self._inference[key] = inf
+        elif inf is None:
             mode = self.inference_mode
             if mode == "auto":
                 from . import fused

@@ -176,3 +176,80 @@ class OracleMAMuZeroNet(nn.Module):
         reward = inverse_support_transform(reward_logits, *self.reward_support)
         value = inverse_support_transform(value_logits, *self.value_support)
         return nxt, reward, value, policy_logits
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The matrix-game network (BASELINE configs[0]): plain MLPs over the concatenated state of all agents.
+def _matrix_mlp(sizes, value_out=False):
+    """Linear -> ReLU -> LayerNorm per layer; `value_out` drops the last ReLU + LayerNorm
+    (reference mlp(): config/matrix/model.py:15-51)."""
+    mods = []
+    for i in range(len(sizes) - 1):
+        mods += [nn.Linear(sizes[i], sizes[i + 1]), nn.ReLU(), nn.LayerNorm(sizes[i + 1])]
+    return nn.Sequential(*(mods[:-2] if value_out else mods))
+
+
+class _MatrixDynamics(nn.Module):  # config/matrix/model.py:86-126
+    def __init__(self, d, na, dyn_layers, rew_layers, rsup):
+        super().__init__()
+        self.fc_dynamic = _matrix_mlp([d + na] + list(dyn_layers) + [d])
+        self.fc_reward = _matrix_mlp([d + na] + list(rew_layers) + [rsup], value_out=True)
+
+
+class _MatrixPrediction(nn.Module):  # config/matrix/model.py:129-166
+    def __init__(self, n, h, a, val_layers, pol_layers, vsup):
+        super().__init__()
+        self.fc_value = _matrix_mlp([n * h] + list(val_layers) + [vsup], value_out=True)
+        self.fc_policy = _matrix_mlp([h] + list(pol_layers) + [a], value_out=True)
+
+
+class OracleMatrixMuZeroNet(nn.Module):
+    """Search-path subset of the reference's matrix-game MAMuZeroNet (config/matrix/model.py:208-368) with the
+    reference's parameter names.  `reward_support` / `value_support` = (min, max); (0, 0) is the scalar head
+    of use_vectorization=False (core/config.py:378-381), whose inverse transform is the identity (:488,495)."""
+
+    def __init__(self, num_agents=2, action_space_size=3, hidden_state_size=64, fc_dynamic_layers=(64, 64),
+                 fc_reward_layers=(32,), fc_value_layers=(32,), fc_policy_layers=(32,), reward_support=(-3, 3),
+                 value_support=(-10, 10)):
+        super().__init__()
+        self.num_agents, self.action_space_size, self.hidden_state_size = num_agents, action_space_size, hidden_state_size
+        self.hidden = hidden_state_size
+        self.reward_support, self.value_support = tuple(reward_support), tuple(value_support)
+        rs, vs = reward_support[1] - reward_support[0] + 1, value_support[1] - value_support[0] + 1
+        d = num_agents * hidden_state_size
+        self.dynamics_network = _MatrixDynamics(d, num_agents * action_space_size, fc_dynamic_layers, fc_reward_layers, rs)
+        self.prediction_network = _MatrixPrediction(num_agents, hidden_state_size, action_space_size, fc_value_layers,
+                                                    fc_policy_layers, vs)
+
+    load_reference_state_dict = OracleMAMuZeroNet.load_reference_state_dict
+
+    def init_like_reference(self, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                w = torch.empty_like(m.weight)
+                nn.init.orthogonal_(w, gain=math.sqrt(2.0), generator=g)
+                m.weight.data.copy_(w)
+                m.bias.data.zero_()
+        return self
+
+    def prediction(self, hidden):  # config/matrix/model.py:163-166, 320-322
+        b = hidden.shape[0]
+        value = self.prediction_network.fc_value(hidden)
+        pol = self.prediction_network.fc_policy(hidden.reshape(-1, self.hidden_state_size))
+        return pol.reshape(b, self.num_agents, self.action_space_size), value
+
+    def dynamics(self, hidden, action):  # config/matrix/model.py:334-345, 118-126
+        b = hidden.shape[0]
+        onehot = F.one_hot(action.long(), num_classes=self.action_space_size).float().view(b, -1)
+        state = self.dynamics_network.fc_dynamic(torch.cat([hidden, onehot], dim=1)) + hidden
+        return state, self.dynamics_network.fc_reward(torch.cat([state, onehot], dim=1))
+
+    def _inv(self, x, sup):
+        return x if sup[1] == sup[0] else inverse_support_transform(x, *sup)
+
+    @torch.no_grad()
+    def recurrent_inference(self, hidden, action):  # config/matrix/model.py:358-368
+        nxt, reward = self.dynamics(hidden, action)
+        policy_logits, value = self.prediction(nxt)
+        return nxt, self._inv(reward, self.reward_support), self._inv(value, self.value_support), policy_logits

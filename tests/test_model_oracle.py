@@ -11,11 +11,15 @@ MODEL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden"
 
 
 def load_model_golden(path):
-    from oracle.model_oracle import OracleMAMuZeroNet
+    from oracle.model_oracle import OracleMAMuZeroNet, OracleMatrixMuZeroNet
 
     z = np.load(path)
     n, a, h, b = [int(x) for x in z["dims"]]
     sd = {k[3:]: z[k] for k in z.files if k.startswith("sd.")}
+    if "supports" in z.files:     # the matrix-game network (config/matrix/model.py)
+        r0, r1, v0, v1 = [int(x) for x in z["supports"]]
+        m = OracleMatrixMuZeroNet(n, a, h, reward_support=(r0, r1), value_support=(v0, v1))
+        return z, m.load_reference_state_dict(sd).eval(), sd, (n, a, h, b)
     m = OracleMAMuZeroNet(n, a, hidden_state_size=h, fc_dynamic_layers=(h, h)).load_reference_state_dict(sd).eval()
     return z, m, sd, (n, a, h, b)
 

@@ -47,18 +47,12 @@ def test_step_path_reproduces_reference_known_answers(built_lib):
     check_kat(*sequential_search(fn, cfg, model, legal=kat_legal()))
 
 
-@pytest.mark.parametrize("mode", ["bf16", "fp32"])
-@pytest.mark.parametrize("cur", [None, 0, 1, 2])
-def test_device_path_replays_bit_exact_through_oracle_tree(built_lib, oracle_built, cur, mode):
-    from mazero_b200.inference import SmacInference
+def device_path_replay(inf, out0, N, A, B, K, S, cur, oracle_built):
+    """Run the on-device search eagerly with every simulation's network outputs recorded, replay them through the CPU
+    oracle tree (bit-exact selections, sampled sets, visit counts, values, Q), then require graph replay == eager."""
     from mazero_b200.mcts_sampled import SampledMCTS
 
-    N, A, B, K, S = 3, 9, 48, 10, 25
     cfg = MockConfig(N, A, S, K)
-    model = smac_model(N, A)
-    inf = SmacInference.from_model(model, device="cuda:0", mode=mode)
-    out0 = root_output(model, B)
-    out0 = out0._replace(hidden_state=out0.hidden_state.cuda())
     factor = np.random.RandomState(5).randint(0, A, size=(B, N)).astype(np.int32)
     legal = (np.random.RandomState(6).rand(B, N, A) < 0.7).astype(np.float32)
     legal[..., 1] = 1
@@ -100,13 +94,26 @@ def test_device_path_replays_bit_exact_through_oracle_tree(built_lib, oracle_bui
     assert int(eager.marginal_visit_count[0, 0].sum()) == S
 
     graphed, _ = run(True, None)
-    graphed2 = None
     for f in eager._fields:
         x, y = getattr(eager, f), getattr(graphed, f)
         if isinstance(x, np.ndarray):
             assert np.array_equal(x, y), f
         else:
             assert x == y, f
+    return eager
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+@pytest.mark.parametrize("cur", [None, 0, 1, 2])
+def test_device_path_replays_bit_exact_through_oracle_tree(built_lib, oracle_built, cur, mode):
+    from mazero_b200.inference import SmacInference
+
+    N, A, B, K, S = 3, 9, 48, 10, 25
+    model = smac_model(N, A)
+    inf = SmacInference.from_model(model, device="cuda:0", mode=mode)
+    out0 = root_output(model, B)
+    out0 = out0._replace(hidden_state=out0.hidden_state.cuda())
+    device_path_replay(inf, out0, N, A, B, K, S, cur, oracle_built)
 
 
 def test_device_path_accepts_reference_style_module(built_lib):
