@@ -48,6 +48,13 @@ SIGNATURES = {
     "maz_dbg_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "maz_infer_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maz_mlp_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
+    # include/maz_turn.h
+    "maz_root_prepare_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "maz_dirichlet_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_ulonglong, C.c_void_p]),
+    "maz_agent_turn_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 if not os.path.exists(LIB_PATH):

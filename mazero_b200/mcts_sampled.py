@@ -20,7 +20,10 @@ from typing import List, NamedTuple, Optional, Tuple
 import numpy as np
 import torch
 
+import ctypes as C
+
 from . import cytree
+from ._lib import check, lib
 from .inference import SmacInference
 from .inference_mlp import MlpInference
 from . import inference_mlp
@@ -41,6 +44,15 @@ class SearchOutput(NamedTuple):  # mcts_sampled.py:12-26
     sampled_mcts_values: List[np.ndarray]
     sampled_rewards: List[np.ndarray]
     sampled_qvalues: List[np.ndarray]
+
+
+class AgentTurnsOutput(NamedTuple):
+    """Result of `SampledMCTS.search_agents`: what the workers' per-agent loops build on the host."""
+    actions: np.ndarray        # (B,N) int32   temp_agent_actions / current_actions
+    policy_dist: np.ndarray    # (B,N,A) f64   marginal_visits / sum   (reanalyze_worker.py:319-320)
+    prob: np.ndarray           # (B,) f64      product over agents of policy_dist[agent, action]   (:334-345)
+    entropy: np.ndarray        # (B,N) f64     base-2 visit entropy of select_action (sample turns)
+    search_outputs: list       # N x SearchOutput
 
 
 class Ragged(Sequence):
@@ -88,6 +100,7 @@ class _DevicePlan:
     def __init__(self, inf: SmacInference, B, K, S, cur, cfg, tau, use_graph=True):
         self.inf, self.B, self.K, self.S, self.cur, self.tau = inf, B, K, S, cur, float(tau)
         self.N, self.A, self.H = inf.N, inf.A, inf.H
+        self.joint = cur is None
         self.Nt = self.N if cur is None else 1  # agents in the tree
         dev = inf.device
         self.dev = dev
@@ -105,7 +118,6 @@ class _DevicePlan:
         self.factor = torch.zeros(B, max(self.N, 1), dtype=i32, device=dev)
         self.rows = torch.arange(B, dtype=torch.int64, device=dev)
         z = lambda *s: torch.zeros(*s, dtype=f32, device=dev)
-        self.root_r, self.root_v = z(B), z(B)
         self.root_p, self.root_b, self.root_n = z(B, self.Nt, self.A), z(B, self.Nt, self.A), z(B, self.Nt, self.A)
         # per-simulation network outputs (fused path writes them in place)
         self.sim_r, self.sim_v = z(B), z(B)
@@ -113,22 +125,74 @@ class _DevicePlan:
         self.graphs = {}   # current_agent_idx (or None) -> captured CUDA graph
         self.use_graph = use_graph
         self.record = None  # when a list: per-simulation injected arrays are appended (parity replay tests)
-        # all readouts live in ONE device buffer mirrored by ONE pinned host buffer: one D2H copy per search
+        f64 = torch.float64
+        # ---- host -> device staging: every small root input lives in ONE pinned buffer (one H2D copy per search) ----
+        T = 1 if cur is None else self.N            # turns served by this plan (sequential-agent mode: one per agent)
+        self.T = T
+        NA = self.N * self.A
+        in_spec = [("rewards", f32, (B,)), ("values", f32, (B,)), ("logits", f32, (B, self.N, self.A)),
+                   ("legal", f32, (B, self.N, self.A)), ("factor_in", i32, (B, self.N))]
+        for t in range(T):    # per-turn block (depends on the host RNG): contiguous, so one H2D copy per turn
+            in_spec += [(f"uniforms{t}", f64, (B,)), (f"noise_raw{t}", f32, (B, self.Nt, self.A)), (f"eps_u{t}", f32, (B,)),
+                        (f"rand_act{t}", i32, (B,))]
+        self.inp, self.inp_np, self.in_flat, self.in_host, off = self._flat(in_spec, dev)
+        self.in_common = (0, off["uniforms0"][0])
+        self.in_turn = [(off[f"uniforms{t}"][0], off[f"rand_act{t}"][1]) for t in range(T)]
+        self.root_r, self.root_v = self.inp["rewards"], self.inp["values"]
+        self.has_legal = False
+        # ---- device -> host: all readouts of all turns + the turn results in ONE buffer / ONE D2H copy -------------
         spec = [("value", f32, (B,)), ("marginal_visit_count", i32, (B, self.Nt, self.A)),
                 ("marginal_priors", f32, (B, self.Nt, self.A)), ("num_children", i32, (B,)),
                 ("actions", i32, (B, K, self.Nt)), ("visit_count", i32, (B, K))]
         spec += [(f, f32, (B, K)) for f in cytree._FLOAT_FIELDS]
         words = sum(int(np.prod(shp)) for _, _, shp in spec)
-        self.out_flat = torch.zeros(words, dtype=i32, device=dev)
-        self.out_host = torch.zeros(words, dtype=i32).pin_memory()
-        self.out, self.out_np = {}, {}
-        o = 0
-        host_np = self.out_host.numpy()
+        words += words & 1
+        out_spec = [(f"t{t}", i32, (words,)) for t in range(T)]
+        out_spec += [("turn_actions", i32, (B, self.N)), ("prob_prod", f64, (B,)),
+                     ("policy_dist", f64, (B, self.N, self.A)), ("entropy", f64, (B, self.N))]
+        self.res, self.res_np, self.res_flat, self.res_host, _ = self._flat(out_spec, dev)
+        self.words = words
+        self.turn_out, self.turn_out_np = [], []
+        for t in range(T):
+            o, d, dn = 0, {}, {}
+            for name, dt, shp in spec:
+                n = int(np.prod(shp))
+                d[name] = self.res[f"t{t}"][o:o + n].view(dt).view(*shp)
+                dn[name] = self.res_np[f"t{t}"][o:o + n].view(np.float32 if dt is f32 else np.int32).reshape(shp)
+                o += n
+            self.turn_out.append(d)
+            self.turn_out_np.append(dn)
+        # single-search view (turn 0): what `run` / bench.py / the sharded all-gather use
+        self.out, self.out_np = self.turn_out[0], self.turn_out_np[0]
+        self.out_flat, self.out_host = self.res["t0"], self.res_host[: words]
+        if cur is not None:
+            # the agents' chosen actions (= `factor` of the later turns) live in the result buffer: written by
+            # k_agent_turn on the device, or copied from the caller's host `factor`
+            self.factor = self.res["turn_actions"]
+
+    @staticmethod
+    def _flat(spec, dev):
+        """One device buffer + one pinned host mirror holding all arrays of `spec` (4-byte words; float64 entries are
+        placed at even word offsets).  Returns (device views, host numpy views, device flat, host flat, offsets)."""
+        f64 = torch.float64
+        npdt = {torch.float32: np.float32, torch.int32: np.int32, torch.float64: np.float64}
+        off, o = {}, 0
         for name, dt, shp in spec:
-            n = int(np.prod(shp))
-            self.out[name] = self.out_flat[o:o + n].view(dt).view(*shp)
-            self.out_np[name] = host_np[o:o + n].view(np.float32 if dt is f32 else np.int32).reshape(shp)
+            n = int(np.prod(shp)) * (2 if dt is f64 else 1)
+            if dt is f64 and o % 2:
+                o += 1
+            off[name] = (o, o + n)
             o += n
+        o += o & 1
+        flat = torch.zeros(o, dtype=torch.int32, device=dev)
+        host = torch.zeros(o, dtype=torch.int32).pin_memory()
+        host_np = host.numpy()
+        dv, hv = {}, {}
+        for name, dt, shp in spec:
+            a, b = off[name]
+            dv[name] = flat[a:b].view(dt).view(*shp)
+            hv[name] = host_np[a:b].view(npdt[dt]).reshape(shp)
+        return dv, hv, flat, host, off
 
     def _simulate(self, s, select_first=True, select_next=False):
         """One simulation.  select_first: run the selection kernel at the start (else the previous simulation's
@@ -188,23 +252,40 @@ class _DevicePlan:
     def graph(self):
         return self.graphs.get(self.cur)
 
-    def run(self, seed, cfg, noise_eps, root_hidden, rewards, values, probs, beta, noises, root_greedy, factor,
-            root_index_offset=0, cur="same"):
-        """root_* host numpy (pinned or not) or device tensors; returns the padded readout dict (host numpy)."""
-        if cur != "same":
-            assert (cur is None) == (self.cur is None), "a plan is either joint or sequential"
-            self.cur = cur
+    # ---- host -> device staging ------------------------------------------------------------------------------
+    def _stream(self):
         stream = torch.cuda.current_stream(self.dev)
         self.tree.set_stream(stream.cuda_stream)
-        cp = lambda dst, src: dst.copy_(src if torch.is_tensor(src) else torch.from_numpy(np.ascontiguousarray(src)), non_blocking=True)
-        cp(self.pool[0], root_hidden.reshape(self.B, -1))
-        cp(self.root_r, rewards); cp(self.root_v, values)
-        cp(self.root_p, probs); cp(self.root_b, beta); cp(self.root_n, noises)
-        if self.cur is not None:
-            cp(self.greedy[0], root_greedy)
-            if factor is not None and self.cur > 0:
-                cp(self.factor[:, : self.cur], factor[:, : self.cur] if torch.is_tensor(factor)
-                   else np.asarray(factor, dtype=np.int32)[:, : self.cur])
+        return stream
+
+    def stage_roots(self, root_hidden, rewards, values, logits, legal, factor=None, cur=None):
+        """Everything that does not depend on the host RNG: the root hidden state goes straight into the pool
+        (asynchronously when pinned), the small arrays into the pinned staging block (copied by `_h2d`)."""
+        B, h = self.B, self.inp_np
+        src = root_hidden if torch.is_tensor(root_hidden) else torch.from_numpy(np.ascontiguousarray(root_hidden))
+        self.pool[0].copy_(src.reshape(B, -1), non_blocking=True)
+        h["rewards"][:] = np.asarray(rewards).reshape(B)
+        h["values"][:] = np.asarray(values).reshape(B)
+        h["logits"][:] = np.asarray(logits).reshape(B, self.N, self.A)
+        self.has_legal = legal is not None
+        if legal is not None:
+            h["legal"][:] = np.asarray(legal).reshape(B, self.N, self.A)
+        if factor is not None and cur:
+            h["factor_in"][:, :cur] = np.asarray(factor)[:, :cur]
+
+    def _h2d(self, a, b):
+        self.in_flat[a:b].copy_(self.in_host[a:b], non_blocking=True)
+
+    # ---- one search, fully asynchronous -------------------------------------------------------------------------
+    def _enqueue_search(self, slot, cur, seed, cfg, noise_eps, root_index_offset):
+        """root preparation -> reset -> prepare -> S simulations -> readout into result slot `slot`."""
+        self.cur = cur
+        stream = self._stream()
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+        check(lib.maz_root_prepare_dev(                                         # mcts_sampled.py:57-106 on the device
+            ptr(self.inp["logits"]), ptr(self.inp["legal"]) if self.has_legal else None, ptr(self.inp[f"noise_raw{slot}"]),
+            self.B, self.N, self.A, -1 if cur is None else int(cur), float(noise_eps), 1.0 / self.tau,
+            ptr(self.root_p), ptr(self.root_b), ptr(self.root_n), ptr(self.greedy[0]), C.c_void_p(stream.cuda_stream)))
 
         def prepare():
             self.tree.reset(seed, float(cfg.tree_value_stat_delta_lb), float(cfg.mcts_rho), float(cfg.mcts_lambda), root_index_offset)
@@ -219,10 +300,56 @@ class _DevicePlan:
         else:
             prepare()
             self._loop()
-        self.tree.readout_device(self.discount, self.out)
+        self.tree.readout_device(self.discount, self.turn_out[slot])
+
+    def run(self, seed, cfg, noise_eps, noise_raw, root_index_offset=0, cur=None):
+        """One search after `stage_roots`: `noise_raw` (B,Nt,A) are the raw Dirichlet draws (host).  Returns the
+        padded readout dict (host numpy)."""
+        assert (cur is None) == self.joint, "a plan is either joint or sequential"
+        self._stream()
+        self.inp_np["noise_raw0"][:] = noise_raw
+        self._h2d(0, self.in_turn[0][1])
+        if cur:
+            self.factor[:, :cur].copy_(self.inp["factor_in"][:, :cur], non_blocking=True)
+        self._enqueue_search(0, cur, seed, cfg, noise_eps, root_index_offset)
         self.out_host.copy_(self.out_flat, non_blocking=True)
         self.tree.check()          # synchronises the stream and surfaces device-side invariant failures
         return {k: v.copy() for k, v in self.out_np.items()}
+
+    # ---- the N sequential-agent turns of one environment step, back to back on the device -------------------------
+    def begin_turns(self):
+        self._stream()
+        self._h2d(*self.in_common)
+
+    def enqueue_turn(self, k, mode, seed, cfg, noise_eps, noise_raw, inv_temperature=1.0, uniforms=None, greedy_epsilon=0.0,
+                     eps_u=None, rand_act=None, root_index_offset=0):
+        """Turn of agent k: its search (factor = the actions chosen on the device in the earlier turns), then the
+        worker's action choice (maz_agent_turn_dev).  Nothing synchronises."""
+        h = self.inp_np
+        h[f"noise_raw{k}"][:] = noise_raw
+        if uniforms is not None:
+            h[f"uniforms{k}"][:] = uniforms
+        inject = eps_u is not None and rand_act is not None
+        if inject:
+            h[f"eps_u{k}"][:] = eps_u
+            h[f"rand_act{k}"][:] = rand_act
+        self._h2d(*self.in_turn[k])
+        self._enqueue_search(k, k, seed, cfg, noise_eps, root_index_offset)
+        o, ptr = self.turn_out[k], (lambda t: C.c_void_p(t.data_ptr()))
+        stream = torch.cuda.current_stream(self.dev)
+        check(lib.maz_agent_turn_dev(
+            int(mode), self.B, self.N, self.A, self.K, int(k), ptr(o["num_children"]), ptr(o["actions"]), ptr(o["visit_count"]),
+            ptr(o["marginal_visit_count"]), ptr(self.inp["legal"]) if self.has_legal else None, float(inv_temperature),
+            ptr(self.inp[f"uniforms{k}"]), float(greedy_epsilon), ptr(self.inp[f"eps_u{k}"]) if inject else None,
+            ptr(self.inp[f"rand_act{k}"]) if inject else None, ptr(self.res["turn_actions"]), ptr(self.res["policy_dist"]),
+            ptr(self.res["prob_prod"]), ptr(self.res["entropy"]), C.c_void_p(stream.cuda_stream)))
+
+    def finish_turns(self):
+        self.res_host.copy_(self.res_flat, non_blocking=True)      # ONE D2H copy for all turns
+        self.tree.check()
+        r = self.res_np
+        outs = [{k: v.copy() for k, v in d.items()} for d in self.turn_out_np]
+        return (outs, r["turn_actions"].copy(), r["policy_dist"].copy(), r["prob_prod"].copy(), r["entropy"].copy())
 
     def _capture(self):
         cur = torch.cuda.current_stream(self.dev)
@@ -320,17 +447,33 @@ class SampledMCTS(object):
 
         batch_rewards, batch_values = host(network_output.reward), host(network_output.value)
         all_logits = host(network_output.policy_logits)
+        assert batch_values.shape == (B, 1) and all_logits.size == B * true_num_agents * A
+        if not add_noise:
+            noise_epsilon = 0.0
+
+        inf = self._device_inference(model, device)
+        plan = None
+        if inf is not None:
+            plan = self._plan(inf, B, current_agent_idx, sampled_tau)
+            # the copies that do not depend on the host RNG are in flight while numpy draws the noise
+            plan.stage_roots(network_output.hidden_state, batch_rewards, batch_values, all_logits, legal_actions_lst, factor,
+                             current_agent_idx)
+
+        # exploration noise (:68-70): drawn even when add_noise is False, one Dirichlet per (root, tree agent)
+        noises = self.np_random.dirichlet([noise_alpha] * A, B * Nt if joint else B).astype(np.float32).reshape(B, Nt, A)
+        seed = self.np_random.choice(256)                                            # :89 (after the Dirichlet)
+        if sampled_actions_res is not None:
+            raise NotImplementedError                                                # :108-109
+        if plan is not None:
+            # root preparation (:57-106) runs on the device (maz_root_prepare_dev)
+            r = plan.run(int(seed), cfg, noise_epsilon, noises, root_index_offset, cur=current_agent_idx)
+            return _output_from_readout(r)
+
         if joint:
             logits = all_logits.reshape(B, Nt, A)
         else:
             logits = all_logits[:, current_agent_idx, :].reshape(B, 1, A)           # mcts_sampled.py:60-61
-        assert batch_values.shape == (B, 1) and logits.shape == (B, Nt, A)
         probs = _softmax_np(logits)                                                  # :64-65
-
-        # exploration noise (:68-70): drawn even when add_noise is False, one Dirichlet per (root, tree agent)
-        noises = self.np_random.dirichlet([noise_alpha] * A, B * Nt if joint else B).astype(np.float32).reshape(B, Nt, A)
-        if not add_noise:
-            noise_epsilon = 0.0
         legal = None
         if legal_actions_lst is not None:                                            # :73-83
             legal = (legal_actions_lst.reshape(B, Nt, A) if joint
@@ -342,10 +485,6 @@ class SampledMCTS(object):
             noises *= legal
             noises += legal * 1e-4
             noises = noises / np.sum(noises, axis=-1, keepdims=True)
-
-        seed = self.np_random.choice(256)                                            # :89 (after the Dirichlet)
-        if sampled_actions_res is not None:
-            raise NotImplementedError                                                # :108-109
         beta = probs * (1 - noise_epsilon) + noises * noise_epsilon                  # :93-100
         beta = beta ** (1 / sampled_tau)
         if legal is not None:
@@ -355,20 +494,61 @@ class SampledMCTS(object):
         batch_rewards = batch_rewards.reshape(B).astype(np.float32)
         batch_values = batch_values.reshape(B).astype(np.float32)
         probs, beta, noises = probs.astype(np.float32), beta.astype(np.float32), noises.astype(np.float32)
-
-        inf = self._device_inference(model, device)
-        if inf is not None:
-            key = (id(inf), B, K, cfg.num_simulations, joint, float(sampled_tau))   # all sequential turns share a plan
-            plan = self._plans.get(key)
-            if plan is None:
-                plan = _DevicePlan(inf, B, K, cfg.num_simulations, current_agent_idx, cfg, sampled_tau, self.use_cuda_graph)
-                self._plans[key] = plan
-            root_greedy = np.argmax(all_logits.reshape(B, true_num_agents, A), axis=-1).astype(np.int32)
-            r = plan.run(int(seed), cfg, noise_epsilon, network_output.hidden_state, batch_rewards, batch_values, probs, beta,
-                         noises, root_greedy, factor, root_index_offset, cur=current_agent_idx)
-            return _output_from_readout(r)
         return self._search_step_path(model, network_output, current_agent_idx, factor, true_num_agents, device, sampled_tau,
                                       seed, noise_epsilon, batch_rewards, batch_values, probs, beta, noises, root_index_offset)
+
+    def _plan(self, inf, B, current_agent_idx, sampled_tau) -> _DevicePlan:
+        cfg = self.config
+        key = (id(inf), B, cfg.sampled_action_times, cfg.num_simulations, current_agent_idx is None, float(sampled_tau))
+        plan = self._plans.get(key)                                                  # all sequential turns share a plan
+        if plan is None:
+            plan = _DevicePlan(inf, B, cfg.sampled_action_times, cfg.num_simulations, current_agent_idx, cfg, sampled_tau,
+                               self.use_cuda_graph)
+            self._plans[key] = plan
+        return plan
+
+    # ---- the workers' per-agent loop as ONE device-resident call ------------------------------------------
+    def search_agents(self, model, network_output, true_num_agents: int, legal_actions_lst: np.ndarray = None,
+                      device: torch.device = None, add_noise: bool = True, sampled_tau: float = 1.0, turn: str = "greedy",
+                      temperature: float = 1.0, greedy_epsilon: float = 0.0, eps_randoms=None,
+                      root_index_offset: int = 0) -> "AgentTurnsOutput":
+        """The N sequential per-agent searches of one environment step (selfplay_worker.py:196-257,
+        reanalyze_worker.py:278-327) without returning to the host in between: agent k's search takes `factor` =
+        the actions agents 0..k-1 chose ON THE DEVICE, and the host synchronises once, after the last agent.
+
+        turn="greedy"  reanalyze: action = argmax(marginal_visits * legal)                     (reanalyze_worker.py:298-317)
+        turn="sample"  self-play: select_action(sampled_visit_count, temperature) with np_random, then eps_greedy_action
+                       (selfplay_worker.py:230-257).  `eps_randoms` = (eps_u (N,B) float32, random_action (N,B) int32) are the
+                       draws `torch.rand_like` / `Categorical(legal).sample()` of core/utils.py:328-330, which depend only
+                       on the legal mask; None = no epsilon-greedy override.
+
+        `self.np_random` is consumed in exactly the reference's order -- per agent: dirichlet, choice(256), then (sample
+        mode) one random_sample per root for np_random.choice inside select_action -- and the host draws agent k+1's
+        numbers while the GPU searches for agent k."""
+        cfg = self.config
+        N, A = int(true_num_agents), cfg.action_space_size
+        inf = self._device_inference(model, device)
+        if inf is None:
+            raise RuntimeError("search_agents needs a network with a device path (SMAC / matrix MAMuZeroNet on a CUDA device)")
+        if turn not in ("greedy", "sample"):
+            raise ValueError(turn)
+        B = network_output.hidden_state.shape[0]
+        host = lambda x: x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
+        noise_epsilon = cfg.root_exploration_fraction if add_noise else 0.0
+        plan = self._plan(inf, B, 0, sampled_tau)
+        plan.stage_roots(network_output.hidden_state, host(network_output.reward), host(network_output.value),
+                         host(network_output.policy_logits), legal_actions_lst)
+        plan.begin_turns()
+        eps_u, rand_act = (None, None) if eps_randoms is None else eps_randoms
+        for k in range(N):
+            noises = self.np_random.dirichlet([cfg.root_dirichlet_alpha] * A, B).astype(np.float32).reshape(B, 1, A)
+            seed = self.np_random.choice(256)
+            u = self.np_random.random_sample(B) if turn == "sample" else None        # B x np_random.choice(n, p=...)
+            plan.enqueue_turn(k, 1 if turn == "sample" else 0, int(seed), cfg, noise_epsilon, noises, 1.0 / temperature, u,
+                              greedy_epsilon, None if eps_u is None else eps_u[k], None if rand_act is None else rand_act[k],
+                              root_index_offset)
+        outs, actions, dist, prob, entropy = plan.finish_turns()
+        return AgentTurnsOutput(actions, dist, prob, entropy, [_output_from_readout(r) for r in outs])
 
     # ---- reference simulation loop with the CUDA tree (any BaseNet) --------------------------------------------
     def _search_step_path(self, model, network_output, cur, factor, true_num_agents, device, sampled_tau, seed,
