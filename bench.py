@@ -281,8 +281,31 @@ def run_ours(args):
 
     # batch_search synchronises internally (it returns numpy); wall-clock == device time here, but keep events
     ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
-    h2d = hidden_host.numel() * 4 + 4 * (2 * B + 3 * B * Nt * A) + (4 * B * N if cur is not None else 0)
+    h2d = hidden_host.numel() * 4 + 4 * plan.in_turn[0][1]      # root hidden state + the pinned staging block
     d2h = plan.out_flat.numel() * 4
+
+    # ---- sequential-agent mode: one environment step = N per-agent searches (selfplay_worker.py:196-257,
+    # reanalyze_worker.py:278-327).  (a) the workers' loop over N batch_search calls with the host choosing each agent's
+    # action in between; (b) SampledMCTS.search_agents: the same N searches back to back on the device, one sync.
+    turns = None
+    if cur is not None:
+        def loop_step(i):
+            acts = np.zeros((B, N), dtype=np.int32)
+            for k in range(N):
+                o = mcts.batch_search(inf, out_host, k, acts[:, :k].copy() if k else None, N, None, dev, add_noise=True,
+                                      root_index_offset=root_off)
+                acts[:, k] = np.argmax(o.marginal_visit_count[:, 0, :], axis=-1)      # reanalyze_worker.py:309
+
+        def fused_step(i):
+            mcts.search_agents(inf, out_host, N, None, dev, add_noise=True, turn="greedy", root_index_offset=root_off)
+
+        fused_step(0)
+        ms_loop = timed(loop_step, args.steps, max(args.warmup, 3))
+        ms_fused = timed(fused_step, args.steps, max(args.warmup, 3))
+        turns = {"unit": UNIT, "agents": N, "host_loop": world * B * S * N / (ms_loop * 1e-3), "host_loop_ms": ms_loop,
+                 "search_agents": world * B * S * N / (ms_fused * 1e-3), "search_agents_ms": ms_fused,
+                 "what": "one environment step = N per-agent searches; host_loop = N x batch_search with the action choice "
+                         "on the host, search_agents = one device-resident call (one host sync)"}
 
     # ---- per-kernel timing of the tree kernels (eager loop, CUDA events around each launch) ---------------
     tot_nodes, last_len, sum_len, sum_exp = plan.tree.stats()
@@ -374,6 +397,8 @@ def run_ours(args):
         "roofline": roofline,
         "roofline_tree": tree_roof,
     }
+    if turns is not None:
+        line["e2e_agent_turns"] = turns
     if not args.no_cpu_baseline and world == 1:
         # bounded sample of the same workload on the host cores (one warm-up + two timed searches)
         Bs = min(B, 1024)

@@ -48,6 +48,8 @@ SIGNATURES = {
     "maz_dbg_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "maz_infer_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maz_mlp_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
+    # include/maz_hostrng.h
+    "maz_legacy_dirichlet": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     # include/maz_turn.h
     "maz_root_prepare_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                        C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -22,7 +22,7 @@ import torch
 
 import ctypes as C
 
-from . import cytree
+from . import cytree, hostrng
 from ._lib import check, lib
 from .inference import SmacInference
 from .inference_mlp import MlpInference
@@ -460,7 +460,8 @@ class SampledMCTS(object):
                              current_agent_idx)
 
         # exploration noise (:68-70): drawn even when add_noise is False, one Dirichlet per (root, tree agent)
-        noises = self.np_random.dirichlet([noise_alpha] * A, B * Nt if joint else B).astype(np.float32).reshape(B, Nt, A)
+        # (hostrng: the same values and the same final generator state as np_random.dirichlet, on all host cores)
+        noises = hostrng.dirichlet_f32(self.np_random, noise_alpha, A, B * Nt if joint else B).reshape(B, Nt, A)
         seed = self.np_random.choice(256)                                            # :89 (after the Dirichlet)
         if sampled_actions_res is not None:
             raise NotImplementedError                                                # :108-109
@@ -541,7 +542,7 @@ class SampledMCTS(object):
         plan.begin_turns()
         eps_u, rand_act = (None, None) if eps_randoms is None else eps_randoms
         for k in range(N):
-            noises = self.np_random.dirichlet([cfg.root_dirichlet_alpha] * A, B).astype(np.float32).reshape(B, 1, A)
+            noises = hostrng.dirichlet_f32(self.np_random, cfg.root_dirichlet_alpha, A, B).reshape(B, 1, A)
             seed = self.np_random.choice(256)
             u = self.np_random.random_sample(B) if turn == "sample" else None        # B x np_random.choice(n, p=...)
             plan.enqueue_turn(k, 1 if turn == "sample" else 0, int(seed), cfg, noise_epsilon, noises, 1.0 / temperature, u,

@@ -1,0 +1,70 @@
+"""CPU: the parallel restatement of numpy's legacy Dirichlet draw (include/maz_hostrng.h) is BIT-identical to
+`RandomState.dirichlet(...).astype(float32)` -- values and final generator state -- for the shapes of every BASELINE
+configuration, odd stream positions, a pending cached Gaussian, and draws that follow."""
+import time
+
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("rows,A,alpha", [(1024 * 3, 9, 0.3), (1024, 9, 0.3), (4096 * 5, 11, 0.3), (512, 18, 0.25),
+                                          (16384, 36, 0.3), (700, 3, 0.9), (64, 8, 0.05)])
+def test_parallel_dirichlet_is_bit_identical_to_numpy(built_lib, rows, A, alpha):
+    from mazero_b200 import hostrng
+
+    for seed in (0, 1, 12345):
+        a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+        for burn in (0, 1, 623, 7):                       # odd word positions, block boundaries
+            a.randint(0, 2**31 - 1, size=burn); b.randint(0, 2**31 - 1, size=burn)
+            ref = a.dirichlet([alpha] * A, rows).astype(np.float32)
+            got = hostrng.dirichlet_f32(b, alpha, A, rows)
+            assert got.dtype == np.float32 and got.shape == (rows, A)
+            assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+            sa, sb = a.get_state(), b.get_state()
+            assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+            assert a.choice(256) == b.choice(256)          # what batch_search draws next (mcts_sampled.py:89)
+
+
+def test_cached_gaussian_and_global_state_are_preserved(built_lib):
+    from mazero_b200 import hostrng
+
+    a, b = np.random.RandomState(3), np.random.RandomState(3)
+    a.standard_normal(); b.standard_normal()               # leaves has_gauss = 1
+    ref = a.dirichlet([0.3] * 9, 1000).astype(np.float32)
+    got = hostrng.dirichlet_f32(b, 0.3, 9, 1000)
+    assert np.array_equal(ref, got) and a.standard_normal() == b.standard_normal()
+    np.random.seed(11)
+    ref = np.random.dirichlet([0.3] * 9, 600).astype(np.float32)
+    nxt = np.random.random_sample()
+    np.random.seed(11)
+    got = hostrng.dirichlet_f32(np.random, 0.3, 9, 600)
+    assert np.array_equal(ref, got) and nxt == np.random.random_sample()
+
+
+def test_unsupported_cases_are_drawn_by_numpy_itself(built_lib):
+    from mazero_b200 import hostrng
+
+    for alpha, rows in ((1.5, 1000), (0.3, 10)):           # alpha >= 1 (Marsaglia-Tsang branch), tiny draws
+        a, b = np.random.RandomState(5), np.random.RandomState(5)
+        assert np.array_equal(a.dirichlet([alpha] * 4, rows).astype(np.float32), hostrng.dirichlet_f32(b, alpha, 4, rows))
+        assert a.random_sample() == b.random_sample()
+
+
+def test_parallel_dirichlet_is_faster_than_numpy(built_lib):
+    from mazero_b200 import hostrng
+
+    rs = np.random.RandomState(0)
+    hostrng.dirichlet_f32(rs, 0.3, 9, 3072)
+
+    def best(fn, n=15):          # best of n: the build container is a noisy, shared host
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    t_np = best(lambda: rs.dirichlet([0.3] * 9, 3072).astype(np.float32))
+    t_par = best(lambda: hostrng.dirichlet_f32(rs, 0.3, 9, 3072))
+    print(f"numpy {t_np * 1e3:.2f} ms, parallel {t_par * 1e3:.2f} ms")
+    assert t_par < t_np
