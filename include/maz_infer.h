@@ -50,6 +50,12 @@ typedef struct maz_infer_desc {
 /* replaces model.recurrent_inference + the driver's softmax/beta (mcts_sampled.py:150-161): one kernel launch */
 int maz_infer_recurrent(const maz_infer_desc *desc, void *cuda_stream);
 
+/* The same computation for SMALL batches (mazero_b200/csrc/infer_hmma.cuh): 32-row tiles on warp-level bf16 MMAs, so
+ * that 1024 roots x 3 agents fill 103 SMs instead of 26 and the per-simulation latency chain is short.  `wpk` and the
+ * chunk tables are in the row-major padded layout of mazero_b200/fused.py::HmmaParams (chunk = [out][K + 8] bf16);
+ * `vec` and all other fields as above. */
+int maz_infer_recurrent_small(const maz_infer_desc *desc, void *cuda_stream);
+
 /* ---- MLP-family network (the reference's matrix-game MAMuZeroNet) --------------------------------------------
  * Replaces, for the search only, config/matrix/model.py:358-368 `recurrent_inference` (= `dynamics` :334-343 /
  * DynamicsNetwork.forward :118-126 + PredictionNetwork.forward :163-166) and the driver's softmax / beta

@@ -7,6 +7,7 @@
 #include "../../include/maz_infer.h"
 #include "umma.cuh"
 #include "infer_fused.cuh"
+#include "infer_hmma.cuh"
 
 using namespace maz;
 using namespace maz::umma;
@@ -122,5 +123,34 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
     cfg.numAttrs = (maz::pdl_mask() & 1) ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fused::k_recurrent_inference, *d);
     if (e != cudaSuccess) return set_last_error(2, std::string("k_recurrent_inference: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+// Small-batch variant (infer_hmma.cuh): 32-row tiles on warp-level MMAs.  `d->wpk` / chunk tables must be in the
+// row-major padded layout of mazero_b200/fused.py::HmmaParams.
+extern "C" int maz_infer_recurrent_small(const maz_infer_desc *d, void *stream)
+{
+    if (!d) return set_last_error(1, "maz_infer_recurrent_small: NULL descriptor");
+    if (d->B <= 0 || d->N <= 0 || d->N > 32 || d->A <= 0 || d->A > 48 || d->KA % 16 || d->KA < d->A || d->NAP != d->KA)
+        return set_last_error(3, "maz_infer_recurrent_small: unsupported shape (agents <= 32, actions <= 48)");
+    if (!d->pool || !d->actions || !d->next_hidden || !d->reward || !d->value || !d->probs || !d->beta || !d->wpk || !d->vec)
+        return set_last_error(1, "maz_infer_recurrent_small: NULL tensor");
+    if (d->vec_floats <= 0 || d->vec_floats % 4) return set_last_error(1, "maz_infer_recurrent_small: vec_floats must be a positive multiple of 4");
+    for (int c = 0; c < MAZ_INFER_NCHUNK; ++c)
+        if (d->chunk_bytes[c] == 0 || d->chunk_bytes[c] > hmma::SLOT_BYTES || d->chunk_bytes[c] % 16 || d->chunk_off[c] % 16)
+            return set_last_error(1, "maz_infer_recurrent_small: bad weight chunk table");
+    const size_t dyn = hmma::smem_bytes(d->KA, d->vec_floats);
+    if (dyn > 227 * 1024) return set_last_error(3, "maz_infer_recurrent_small: parameters do not fit in shared memory");
+    static size_t configured = 0;
+    if (dyn > configured) {
+        cudaError_t e = cudaFuncSetAttribute(hmma::k_recurrent_inference_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return set_last_error(2, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+        configured = dyn;
+    }
+    const int rpt = hmma::TM / d->N;
+    const int tiles = (d->B + rpt - 1) / rpt;
+    hmma::k_recurrent_inference_small<<<(unsigned)tiles, hmma::NTHREADS, dyn, static_cast<cudaStream_t>(stream)>>>(*d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_last_error(2, std::string("k_recurrent_inference_small: ") + cudaGetErrorString(e));
     return 0;
 }

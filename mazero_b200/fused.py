@@ -4,6 +4,7 @@ in the order the kernel consumes them, and (b) one fp32 vector of biases / Layer
 table / value & reward heads; fills the launch descriptor.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -45,6 +46,23 @@ def pack_operand(w):
         src_chunk = ar[None, :] ^ ar[:, None]                                    # [r8, position] -> chunk j = position ^ r8
         return t[:, :, ar[:, None], src_chunk, :].contiguous().view(-1)
     return wb.view(r // 8, 8, k // 8, 8).permute(0, 2, 1, 3).contiguous().view(-1)
+
+
+def pack_rowmajor(w):
+    """[rows, K] fp32 -> bf16 [rows][K + 8]: the small-batch kernel's weight layout (csrc/infer_hmma.cuh): row-major with 16
+    bytes of padding per row so that ldmatrix reads are bank-conflict free."""
+    r, k = w.shape
+    assert r % 16 == 0 and k % 16 == 0, (r, k)
+    out = torch.zeros(r, k + 8, dtype=torch.bfloat16, device=w.device)
+    out[:, :k] = w.to(torch.bfloat16)
+    return out.view(-1)
+
+
+def _interleave_gnn(stacked):
+    """Stacked GraphNetNN weight [gc (64 rows); nn (64 rows)] -> the column warp q of the small-batch kernel gets, in its 32
+    output columns, gc[16q:16q+16] then nn[16q:16q+16] (both halves of the 16 features it normalises)."""
+    gc, nn = stacked[:GH], stacked[GH:]
+    return torch.cat([torch.cat([gc[16 * q:16 * q + 16], nn[16 * q:16 * q + 16]]) for q in range(4)])
 
 
 def _padcols(w, k):
@@ -105,7 +123,7 @@ class FusedParams:
                    g(d + "fc_dynamic.6.weight")]
         r = d + "reward_predictor."
         wr1 = torch.cat([g(r + "gc1.lin_layer.weight"), g(r + "nn_gc1.weight")], 0)      # (128, 128 + A)
-        chunks += [wr1[:, :H], _padcols(wr1[:, H:H + A], KA)]
+        chunks += [wr1[:, :H], _padcols(wr1[:, H:H + A], KA)]                            # chunks 25, 26
         chunks.append(torch.cat([g(r + "gc2.lin_layer.weight"), g(r + "nn_gc2.weight")], 0))
         v = p + "value_predictor."
         chunks.append(torch.cat([g(v + "gc1.lin_layer.weight"), g(v + "nn_gc1.weight")], 0))
@@ -113,6 +131,22 @@ class FusedParams:
         chunks.append(g(p + "fc_policy.0.weight"))                     # (32, 128)
         chunks.append(_padrows(g(p + "fc_policy.3.weight"), KA))       # (KA, 32)
         assert len(chunks) == NCHUNK
+        # small-batch kernel: same 32 matrices, row-major padded, heads merged into two stages
+        # (L1: reward h / reward onehot / value / policy.0; L2: reward / value / policy.3), GNN rows interleaved
+        c = chunks
+        hm = c[:25] + [_interleave_gnn(c[25]), _interleave_gnn(c[26]), _interleave_gnn(c[28]), c[30],
+                       _interleave_gnn(c[27]), _interleave_gnn(c[29]), c[31]]
+        hp = [pack_rowmajor(t.contiguous()) for t in hm]
+        offs_h, o = [], 0
+        for t in hp:
+            offs_h.append(o)
+            o += t.numel() * 2
+        wpk_h = torch.cat(hp)
+        self.chunk_off_h, self.chunk_bytes_h = offs_h, [t.numel() * 2 for t in hp]
+        if getattr(self, "wpk_h", None) is None:
+            self.wpk_h = wpk_h
+        else:
+            self.wpk_h.copy_(wpk_h)
         packed = [pack_operand(c.contiguous()) for c in chunks]
         offs, o = [], 0
         for t in packed:
@@ -157,7 +191,7 @@ class FusedParams:
             self.vec.copy_(vecf)
 
     def desc(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None, logits_out=None,
-             tree_agents=None, cur=-1, inv_tau=1.0, dbg_clock=None):
+             tree_agents=None, cur=-1, inv_tau=1.0, dbg_clock=None, small=False):
         ptr = lambda t: (t.data_ptr() if t is not None else None)
         dsc = InferDesc()
         dsc.B, dsc.N, dsc.A, dsc.KA, dsc.NAP = int(B), self.N, self.A, self.KA, self.KA
@@ -169,14 +203,30 @@ class FusedParams:
         dsc.dbg_clock = ptr(dbg_clock)
         import os as _os
         dsc.dbg_flags = int(_os.environ.get('MAZ_DBG_FLAGS', '0'))
-        dsc.wpk, dsc.vec, dsc.vec_floats = self.wpk.data_ptr(), self.vec.data_ptr(), self.vec.numel()
+        dsc.wpk, dsc.vec, dsc.vec_floats = (self.wpk_h if small else self.wpk).data_ptr(), self.vec.data_ptr(), self.vec.numel()
+        co, cb = (self.chunk_off_h, self.chunk_bytes_h) if small else (self.chunk_off, self.chunk_bytes)
         for i in range(NCHUNK):
-            dsc.chunk_off[i], dsc.chunk_bytes[i] = self.chunk_off[i], self.chunk_bytes[i]
+            dsc.chunk_off[i], dsc.chunk_bytes[i] = co[i], cb[i]
         o = self.off
         dsc.o_bin, dsc.o_pos, dsc.o_layer, dsc.o_dyn = o["bin"], o["pos"], o["layer"], o["dyn"]
         dsc.o_rg, dsc.o_vg, dsc.o_pol = o["rg"], o["vg"], o["pol"]
         return dsc
 
 
-def launch(dsc, stream_ptr):
-    check(lib.maz_infer_recurrent(C.byref(dsc), C.c_void_p(stream_ptr)))
+# Which kernel: the tcgen05 kernel needs 128-row tiles (a CTA per 4*floor(32/N) roots), the small-batch kernel 32-row tiles
+# (a CTA per floor(32/N) roots) but re-reads the 0.9 MB of weights from L2 once per CTA.  MAZ_INFER_KERNEL=small|tcgen05
+# forces one; "auto" takes the small-batch kernel while its grid stays within SMALL_MAX_TILES.
+SMALL_MAX_TILES = int(os.environ.get("MAZ_INFER_SMALL_MAX_TILES", "296"))
+
+
+def use_small(B, N):
+    mode = os.environ.get("MAZ_INFER_KERNEL", "auto")
+    if mode in ("small", "tcgen05"):
+        return mode == "small"
+    rpt = 32 // N
+    return (B + rpt - 1) // rpt <= SMALL_MAX_TILES
+
+
+def launch(dsc, stream_ptr, small=False):
+    fn = lib.maz_infer_recurrent_small if small else lib.maz_infer_recurrent
+    check(fn(C.byref(dsc), C.c_void_p(stream_ptr)))

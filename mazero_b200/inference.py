@@ -124,14 +124,15 @@ class SmacInference:
             self.fused.repack(self._params)
 
     def recurrent_fused(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None,
-                        logits_out=None, tree_agents=None, cur=-1, inv_tau=1.0, stream=None, dbg_clock=None):
+                        logits_out=None, tree_agents=None, cur=-1, inv_tau=1.0, stream=None, dbg_clock=None, kernel=None):
         """One launch of the fused kernel: gather parent hidden from `pool` by `idx_x`, recurrent_inference,
         inverse support transforms, softmax / beta of the tree agents.  Everything stays on the device."""
         from . import fused
 
+        small = fused.use_small(int(B), self.N) if kernel is None else (kernel == "small")
         dsc = self.fused.desc(B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy, logits_out,
-                              tree_agents, cur, inv_tau, dbg_clock)
-        fused.launch(dsc, (stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream)
+                              tree_agents, cur, inv_tau, dbg_clock, small=small)
+        fused.launch(dsc, (stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream, small)
 
     # ---- pieces ----------------------------------------------------------------------------------------
     @staticmethod

@@ -29,10 +29,12 @@ def test_umma_gemm_stage(built_lib, n, k):
     assert err < 2e-3, f"max abs err {err}"     # fp32 accumulation-order noise only
 
 
+@pytest.mark.parametrize("kernel", ["tcgen05", "small"])
 @pytest.mark.parametrize("N,A,B", [(3, 9, 100), (5, 11, 70), (10, 18, 33), (27, 36, 9), (1, 5, 130), (2, 3, 16), (2, 40, 20),
                                    (30, 17, 5), (3, 9, 1)])
-def test_fused_recurrent_inference_matches_fp32_reference(built_lib, N, A, B):
-    """bf16 tensor-core kernel vs the plain fp32 torch forward (same weights).  Tolerance: bf16 operand
+def test_fused_recurrent_inference_matches_fp32_reference(built_lib, N, A, B, kernel):
+    """bf16 tensor-core kernels (tcgen05 128-row tiles; small-batch 32-row tiles on warp-level MMAs) vs the plain fp32 torch
+    forward (same weights).  Tolerance: bf16 operand
     rounding (2^-8 relative) through ~20 chained GEMMs -> 2% of each tensor's dynamic range (max |ref|,
     at least 1); probabilities 1e-2 absolute."""
     from mazero_b200.inference import SmacInference
@@ -57,7 +59,7 @@ def test_fused_recurrent_inference_matches_fp32_reference(built_lib, N, A, B):
     beta = torch.full((B, N, A), float("nan"), device=dev)
     logits = torch.full((B, N, A), float("nan"), device=dev)
     greedy = torch.full((B, N), -1, dtype=torch.int32, device=dev)
-    fus.recurrent_fused(B, pool, idx, act, nxt, rew, val, probs, beta, greedy, logits)
+    fus.recurrent_fused(B, pool, idx, act, nxt, rew, val, probs, beta, greedy, logits, kernel=kernel)
     torch.cuda.synchronize()
     for name, x, y, rel in (("next_hidden", nxt, nxt_ref, 2e-2), ("policy_logits", logits, log_ref, 2e-2),
                             ("reward", rew, rew_ref, 4e-2), ("value", val, val_ref, 4e-2),   # + the steep inv_h transform
@@ -75,7 +77,7 @@ def test_fused_recurrent_inference_matches_fp32_reference(built_lib, N, A, B):
     cur = N - 1
     p1 = torch.full((B, 1, A), float("nan"), device=dev)
     b1 = torch.full((B, 1, A), float("nan"), device=dev)
-    fus.recurrent_fused(B, pool, idx, act, nxt, rew, val, p1, b1, None, None, tree_agents=1, cur=cur, inv_tau=0.5)
+    fus.recurrent_fused(B, pool, idx, act, nxt, rew, val, p1, b1, None, None, tree_agents=1, cur=cur, inv_tau=0.5, kernel=kernel)
     torch.cuda.synchronize()
     assert torch.allclose(p1[:, 0], probs[:, cur], atol=1e-6)
     bt = probs[:, cur] ** 0.5
