@@ -139,7 +139,7 @@ extern "C" int maz_infer_recurrent_small(const maz_infer_desc *d, void *stream)
     for (int c = 0; c < MAZ_INFER_NCHUNK; ++c)
         if (d->chunk_bytes[c] == 0 || d->chunk_bytes[c] > hmma::SLOT_BYTES || d->chunk_bytes[c] % 16 || d->chunk_off[c] % 16)
             return set_last_error(1, "maz_infer_recurrent_small: bad weight chunk table");
-    const size_t dyn = hmma::smem_bytes(d->KA, d->vec_floats);
+    const size_t dyn = hmma::smem_bytes(d->vec_floats);
     if (dyn > 227 * 1024) return set_last_error(3, "maz_infer_recurrent_small: parameters do not fit in shared memory");
     static size_t configured = 0;
     if (dyn > configured) {
