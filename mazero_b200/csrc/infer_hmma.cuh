@@ -422,15 +422,17 @@ template <int NN>
 __device__ __forceinline__ void attention_small(uint32_t qbase, int r0, int hh, const float (&q)[16], float (&o)[16])
 {
     float s[NN];
-    uint32_t vw[NN][8];
+    uint32_t kw[NN][8], vw[NN][8];
 #pragma unroll
     for (int j = 0; j < NN; ++j) {
         const uint32_t kr = qbase + (uint32_t)(r0 + j) * LDQ + H * 2 + hh * 32;
-        uint32_t kw[8];
-        lds32B(kr, kw);
+        lds32B(kr, kw[j]);
         lds32B(kr + H * 2, vw[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NN; ++j) {
         float k[16];
-        unpack16(kw, k);
+        unpack16(kw[j], k);
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; i += 2) { a += q[i] * k[i]; b += q[i + 1] * k[i + 1]; }
@@ -623,17 +625,42 @@ __device__ __forceinline__ void gnn_phase_a(const float (&acc)[4][4], const Thr 
         sts2f(G + 4u * (th.rB * LDG + f0 + 8 * tl), acc[tl][2] + bg.x, acc[tl][3] + bg.y);
     }
 }
+// sums over the NN agent rows of my two roots: all loads are issued before the first add (the loads are volatile and the
+// SM issues in order: a load that is consumed right away exposes its full latency)
+template <int NN>
+__device__ __forceinline__ void agent_sums(uint32_t G, int f0, int r0A, int r0B, float2 (&sa)[2], float2 (&sc)[2])
+{
+    float2 a[NN][2], c[NN][2];
+#pragma unroll
+    for (int j = 0; j < NN; ++j)
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl) {
+            a[j][tl] = lds2f(G + 4u * ((r0A + j) * LDG + f0 + 8 * tl));
+            c[j][tl] = lds2f(G + 4u * ((r0B + j) * LDG + f0 + 8 * tl));
+        }
+#pragma unroll
+    for (int j = 0; j < NN; ++j)
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl) {
+            sa[tl].x += a[j][tl].x; sa[tl].y += a[j][tl].y; sc[tl].x += c[j][tl].x; sc[tl].y += c[j][tl].y;
+        }
+}
 __device__ __forceinline__ void gnn_phase_b(const float (&acc)[4][4], const Thr &th, uint32_t G, uint32_t b, uint32_t stat, int N, int r0A,
                                             int r0B, float (&y)[2][4])
 {
     const int f0 = 16 * th.nq + 2 * th.t;
     float2 sa[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, sc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll 3
-    for (int j = 0; j < N; ++j) {
-#pragma unroll
-        for (int tl = 0; tl < 2; ++tl) {
-            const float2 a = lds2f(G + 4u * ((r0A + j) * LDG + f0 + 8 * tl)), c = lds2f(G + 4u * ((r0B + j) * LDG + f0 + 8 * tl));
-            sa[tl].x += a.x; sa[tl].y += a.y; sc[tl].x += c.x; sc[tl].y += c.y;
+    switch (N) {                       // CTA-uniform
+        case 1: agent_sums<1>(G, f0, r0A, r0B, sa, sc); break;
+        case 2: agent_sums<2>(G, f0, r0A, r0B, sa, sc); break;
+        case 3: agent_sums<3>(G, f0, r0A, r0B, sa, sc); break;
+        case 4: agent_sums<4>(G, f0, r0A, r0B, sa, sc); break;
+        default: {
+            int j = 0;
+#pragma unroll 1
+            for (; j + 4 <= N; j += 4) agent_sums<4>(G, f0, r0A + j, r0B + j, sa, sc);
+#pragma unroll 1
+            for (; j < N; ++j) agent_sums<1>(G, f0, r0A + j, r0B + j, sa, sc);
         }
     }
 #pragma unroll
@@ -747,6 +774,11 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
     const uint32_t sb = sbase();
     const int n0 = 32 * th.nq, ldg = (GH + PAD) * 2;
     const int N = d.N, A = d.A, tid = threadIdx.x;
+    int hs_n = 40;
+    const bool hs_on = d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0;
+#define HS() \
+    if (hs_on && hs_n < 64) d.dbg_clock[hs_n++] = clock64();
+    HS();
     float aR[4][4], aV[4][4], aP[2][4];
     zero<4>(aR); zero<4>(aV); zero<2>(aP);
     uint32_t w = ring.acquire();
@@ -761,6 +793,7 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
     ring.release(th.lane);
     const uint32_t G = sb + OFF_Q, stat = sb + OFF_STAT, pr = sb + OFF_P + 4u * (d.o_rg + 128), pvv = sb + OFF_P + 4u * (d.o_vg + 128);
     const uint32_t PL = G + 4u * PL0;
+    HS();
     // phase A
     gnn_phase_a(aR, th, G + 4u * G_R, pr);
     gnn_phase_a(aV, th, G + 4u * G_V, pvv);
@@ -775,11 +808,13 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
         }
     }
     cta_sync();
+    HS();
     // phase B
     const int r0A = row_info(th.rA).r0, r0B = row_info(th.rB).r0;
     float yR[2][4], yV[2][4];
     gnn_phase_b(aR, th, G + 4u * G_R, pr, stat, N, r0A, r0B, yR);
     gnn_phase_b(aV, th, G + 4u * G_V, pvv, stat + TM * 32, N, r0A, r0B, yV);
+    HS();
     {   // policy outputs: 8 threads per row (softmax, beta, greedy)
         const int r = tid >> 3, sub = tid & 7;
         const RowInfo ri = row_info(r);
@@ -796,6 +831,7 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
             const int oa = __shfl_xor_sync(0xffffffffu, am, o);
             if (om > m || (om == m && oa < am)) { m = om; am = oa; }
         }
+        HS();
         const bool unit_tau = (d.inv_tau == 1.0f);
         float s = 0.f, sbeta = 0.f;
         for (int a = sub; a < A; a += 8) {
@@ -808,6 +844,7 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
             s += __shfl_xor_sync(0xffffffffu, s, o);
             sbeta += __shfl_xor_sync(0xffffffffu, sbeta, o);
         }
+        HS();
         if (ri.valid) {
             if (d.greedy && sub == 0) d.greedy[(size_t)ri.root * N + ri.agent] = am;
             const int ta = (d.cur < 0) ? ri.agent : (ri.agent == d.cur ? 0 : -1);
@@ -824,7 +861,9 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
             }
         }
     }
+    HS();
     cta_sync();
+    HS();
     // phase C: normalised features (fp32) -> Y (over G, which nobody reads any more)
     gnn_phase_c(th, stat, yR);
     gnn_phase_c(th, stat + TM * 32, yV);
@@ -837,20 +876,30 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
         sts2f(G + 4u * (Y_V + th.rB * GH + f), yV[tl][2], yV[tl][3]);
     }
     cta_sync();
+    HS();
     // phase D: mean over the agents of a root -> pooled[kind][root][f] (fp32) in the X + T tiles (free since the GEMMs above)
     const int rpt = TM / N;
     const uint32_t POOL = sb + OFF_X;
     const float invn = 1.f / (float)N;
     for (int i = tid; i < 2 * rpt * (GH / 2); i += NCONS) {
-        const int f2 = i % (GH / 2), rest = i / (GH / 2), rl = rest % rpt, kind = rest / rpt;
+        const int f2 = i & (GH / 2 - 1), rest = i >> 5, kind = rest >= rpt ? 1 : 0, rl = rest - kind * rpt;
+        const uint32_t src = G + 4u * ((kind ? Y_V : Y_R) + (rl * N) * GH + 2 * f2);
         float2 s = make_float2(0.f, 0.f);
-        for (int j = 0; j < N; ++j) {
-            const float2 v = lds2f(G + 4u * ((kind ? Y_V : Y_R) + (rl * N + j) * GH + 2 * f2));
+        int j = 0;
+#pragma unroll 1
+        for (; j + 3 <= N; j += 3) {
+            const float2 v0 = lds2f(src + 4u * (j * GH)), v1 = lds2f(src + 4u * ((j + 1) * GH)), v2 = lds2f(src + 4u * ((j + 2) * GH));
+            s.x += v0.x + v1.x + v2.x; s.y += v0.y + v1.y + v2.y;
+        }
+#pragma unroll 1
+        for (; j < N; ++j) {
+            const float2 v = lds2f(src + 4u * (j * GH));
             s.x += v.x; s.y += v.y;
         }
         sts2f(POOL + 4u * ((kind * rpt + rl) * GH + 2 * f2), s.x * invn, s.y * invn);
     }
     cta_sync();
+    HS();
     // phase E: logits of the 64 -> 11 heads, thread = (root, kind, k), weights from the padded copy (conflict-free float4 rows)
     const uint32_t LG = sb + OFF_STAT;                             // [rpt][2][12] floats (the statistics are consumed)
     for (int i = tid; i < rpt * 2 * SUP; i += NCONS) {
@@ -858,21 +907,30 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
         const uint32_t pv = POOL + 4u * ((kind * rpt + rl) * GH), vw = sb + OFF_VP + 4u * ((kind * SUP + k) * LDV);
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int f = 0; f < GH; f += 8) {
-            const float4 a0 = lds4v(pv + 4u * f), a1 = lds4v(pv + 4u * f + 16u);
-            const float4 w0 = lds4(vw + 4u * f), w1 = lds4(vw + 4u * f + 16u);
-            s0 += a0.x * w0.x + a0.y * w0.y + a0.z * w0.z + a0.w * w0.w;
-            s1 += a1.x * w1.x + a1.y * w1.y + a1.z * w1.z + a1.w * w1.w;
+        for (int f = 0; f < GH; f += 32) {          // 8 volatile loads in flight, then the math
+            float4 a[8], wv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = lds4v(pv + 4u * (f + 4 * q));
+#pragma unroll
+            for (int q = 0; q < 8; ++q) wv[q] = lds4(vw + 4u * (f + 4 * q));
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+                s0 += a[q].x * wv[q].x + a[q].y * wv[q].y + a[q].z * wv[q].z + a[q].w * wv[q].w;
+                s1 += a[q + 1].x * wv[q + 1].x + a[q + 1].y * wv[q + 1].y + a[q + 1].z * wv[q + 1].z + a[q + 1].w * wv[q + 1].w;
+            }
         }
         const float bias = lds1(sb + OFF_P + 4u * ((kind ? d.o_vg : d.o_rg) + 256 + SUP * GH + k));
         sts1f(LG + 4u * ((rl * 2 + kind) * 12 + k), s0 + s1 + bias);
     }
     cta_sync();
+    HS();
     if (tid < rpt * 2) {
         const int rl = tid >> 1, kind = tid & 1;
         const int root = blockIdx.x * rpt + rl;
         if (root < d.B) (kind ? d.value : d.reward)[root] = support_to_scalar(LG + 4u * ((rl * 2 + kind) * 12));
     }
+    HS();
+#undef HS
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_small(const __grid_constant__ Desc d)

@@ -27,3 +27,6 @@ names = ["gather", "params wait", "inproj"] + [f"L{l} {s}" for l in range(3) for
 for i, n in enumerate(names):
     print(f"{n:28s} {c[i + 1] - c[i]:7d} cycles")
 print("total", c[len(names)] - c[0], "cycles")
+hs = ["gemms", "phase A + barrier", "B: graph sums", "policy: argmax", "policy: exp sums", "policy: writes", "barrier", "C: normalise + Y + barrier",
+      "D: pool + barrier", "E: logits + barrier", "F: scalars"]
+print("heads2 phases:", {n: int(c[41 + i] - c[40 + i]) for i, n in enumerate(hs)})
