@@ -366,11 +366,17 @@ def run_ours(args):
                  "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_tree, "launch_ms": ms_tree}
     if ms_inf is not None:   # the dominant kernel of the step (~75 % of the GPU time): tensor-pipe roofline
         flop = B * FLOP_PER_ROOT.get(args.workload, 0.0)
-        roofline = {"bound": "tensor", "kernel": "k_recurrent_inference", "achieved": flop / (ms_inf * 1e-3) / 1e12,
+        from mazero_b200 import fused as _fused
+        small = _fused.use_small(B, N)
+        roofline = {"bound": "tensor", "kernel": "k_recurrent_inference_small" if small else "k_recurrent_inference",
+                    "achieved": flop / (ms_inf * 1e-3) / 1e12,
                     "peak": bf16_peak(), "unit": "TFLOP/s", "frac": flop / (ms_inf * 1e-3) / 1e12 / bf16_peak(),
-                    "traffic": traffic.get("k_recurrent_inference:3m:joint"), "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)",
+                    "traffic": traffic.get("k_recurrent_inference_small:3m:joint" if small else "k_recurrent_inference:3m:joint"),
+                    "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)",
                     "algorithmic_flop_per_launch": flop, "launch_ms": ms_inf,
-                    "note": "latency-bound 25-stage chain per 128-row tile; see DESIGN.md section 5"}
+                    "note": ("small-batch kernel: 32-row tiles on warp-level MMAs, one launch per simulation; bound by the dependent "
+                             "stage chain of a tile (instruction issue / latency), not by the tensor pipe; see DESIGN.md section 5")
+                            if small else "latency-bound 25-stage chain per 128-row tile; see DESIGN.md section 5"}
     else:
         roofline = tree_roof
 

@@ -55,6 +55,9 @@ int maz_infer_recurrent(const maz_infer_desc *desc, void *cuda_stream);
  * chunk tables are in the row-major padded layout of mazero_b200/fused.py::HmmaParams (chunk = [out][K + 8] bf16);
  * `vec` and all other fields as above. */
 int maz_infer_recurrent_small(const maz_infer_desc *desc, void *cuda_stream);
+/* number of column groups the small-batch kernel was compiled for (4 or 8): the stacked graph-net weights are
+ * interleaved in groups of 64 / nq features (gc rows, then nn rows) by the host-side packer. */
+int maz_infer_small_nq(void);
 
 /* ---- MLP-family network (the reference's matrix-game MAMuZeroNet) --------------------------------------------
  * Replaces, for the search only, config/matrix/model.py:358-368 `recurrent_inference` (= `dynamics` :334-343 /

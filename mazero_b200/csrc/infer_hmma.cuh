@@ -31,7 +31,15 @@ using namespace umma;
 constexpr int H = 128, NHEAD = 8, HD = 16, GH = 64, PH = 32, SUP = 11, NLAYER = 3;
 constexpr int NCHUNK = MAZ_INFER_NCHUNK, NSLOT = 3;
 constexpr int TM = 32;                       // token rows per CTA
-constexpr int NCONS = 256, NTHREADS = NCONS + 32;   // 8 compute warps + 1 producer warp
+#ifndef MAZ_HMMA_NQ
+#define MAZ_HMMA_NQ 4
+#endif
+constexpr int NQ = MAZ_HMMA_NQ;              // column groups: a warp owns 16 rows x (128 / NQ) columns of a 128-wide stage
+constexpr int NT = H / NQ / 8;               // n8 tiles per warp in a 128-wide stage
+constexpr int GT = GH / NQ / 8;              // n8 tiles per warp and half (gc | nn) of a stacked graph-net GEMM
+constexpr int CW = H / NQ, FW = GH / NQ;     // columns / graph features per warp
+static_assert(NQ == 4 || NQ == 8, "NQ");
+constexpr int NCONS = 64 * NQ, NTHREADS = NCONS + 32;   // 2*NQ compute warps + 1 producer warp
 constexpr int PAD = 8;                       // bf16 elements of row padding (16 bytes: ldmatrix rows land in distinct banks)
 constexpr int LDA = (H + PAD) * 2;           // bytes per activation row
 constexpr int LDQ = (3 * H + PAD) * 2;       // bytes per q|k|v row
@@ -52,8 +60,9 @@ constexpr uint32_t OFF_HH = OFF_T + TM * LDA;                    // parent hidde
 constexpr uint32_t OFF_ONE = OFF_HH + TM * LDA;                  // one-hot joint action     [TM][LDO]
 constexpr uint32_t OFF_PH = OFF_ONE + TM * LDO;                  // policy hidden            [TM][LDP]
 constexpr uint32_t OFF_Q = OFF_PH + TM * LDP;                    // q|k|v rows (layers) / fp32 scratch of the heads
-constexpr uint32_t OFF_STAT = OFF_Q + TM * LDQ;                  // row statistics, 3 sets   [3][TM][4] float2
-constexpr uint32_t OFF_VP = OFF_STAT + 3 * TM * 4 * 8;           // padded reward / value head weights [2][SUP][LDV] fp32
+constexpr uint32_t OFF_STAT = OFF_Q + TM * LDQ;                  // row statistics, 3 sets   [3][TM][NQ] float2
+constexpr uint32_t STAT_SET = TM * NQ * 8;                       // bytes per set
+constexpr uint32_t OFF_VP = OFF_STAT + 3 * TM * NQ * 8;           // padded reward / value head weights [2][SUP][LDV] fp32
 constexpr uint32_t OFF_ROW = OFF_VP + 2 * SUP * LDV * 4;         // row table                [TM] RowInfo
 constexpr uint32_t OFF_W = ((OFF_ROW + TM * 16 + 127) / 128) * 128;   // weight ring         [NSLOT][SLOT_BYTES]
 constexpr uint32_t OFF_P = OFF_W + NSLOT * SLOT_BYTES;           // fp32 parameters (d.vec)
@@ -63,7 +72,7 @@ constexpr int Y_R = 0, Y_V = TM * GH;                            // normalised l
 constexpr int PL0 = 2 * TM * LDG;                                // policy logits                          [TM][48]
 static_assert((PL0 + TM * 48) * 4 <= TM * LDQ, "heads scratch must fit in the q|k|v region");
 static_assert(2 * TM * GH * 4 <= 2 * TM * LDA, "pooled features must fit in the X + T tiles");
-static_assert(TM * 2 * 12 * 4 <= 3 * TM * 4 * 8, "head logits must fit in the statistics region");
+static_assert(TM * 2 * 12 * 4 <= 3 * TM * NQ * 8, "head logits must fit in the statistics region");
 
 using Desc = ::maz_infer_desc;
 
@@ -111,8 +120,8 @@ __device__ __forceinline__ float4 lds4v(uint32_t saddr)   // ordered with the ba
     return v;
 }
 
-// who am I inside the 8 compute warps: warp = nq*2 + mt; the warp owns rows [16*mt, +16) and, of a 128-wide stage,
-// columns [32*nq, +32) as four n8 tiles.  Fragment element acc[nt][2*hf + j] = (row 16*mt + g + 8*hf, col n0 + 8*nt + 2*t + j).
+// who am I inside the 2*NQ compute warps: warp = nq*2 + mt; the warp owns rows [16*mt, +16) and, of a 128-wide stage,
+// columns [CW*nq, +CW) as NT n8 tiles.  Fragment element acc[nt][2*hf + j] = (row 16*mt + g + 8*hf, col n0 + 8*nt + 2*t + j).
 struct Thr {
     int lane, warp, g, t, mt, nq, rA, rB;
     uint32_t a_off, w_off;      // per-lane parts of the ldmatrix row addresses
@@ -240,7 +249,7 @@ __device__ __forceinline__ void relu(float (&acc)[NT][4])
 }
 
 // (sum, sum of squares) of rows rA / rB over this warp's NT tiles, reduced over the quad; lane t == 0 writes slot nq of
-// `stat` ([TM][4] float2, shared address).  After a cta_sync, stats_read gives (mean, rstd) over the whole row.
+// `stat` ([TM][NQ] float2, shared address).  After a cta_sync, stats_read gives (mean, rstd) over the whole row.
 template <int NT>
 __device__ __forceinline__ void stats_write(const float (&v)[NT][4], const Thr &th, uint32_t stat)
 {
@@ -256,35 +265,39 @@ __device__ __forceinline__ void stats_write(const float (&v)[NT][4], const Thr &
         s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
     }
     if (th.t == 0) {
-        sts2f(stat + (uint32_t)(th.rA * 4 + th.nq) * 8u, s0, q0);
-        sts2f(stat + (uint32_t)(th.rB * 4 + th.nq) * 8u, s1, q1);
+        sts2f(stat + (uint32_t)(th.rA * NQ + th.nq) * 8u, s0, q0);
+        sts2f(stat + (uint32_t)(th.rB * NQ + th.nq) * 8u, s1, q1);
     }
 }
 __device__ __forceinline__ void stats_read(uint32_t stat, int row, float inv_width, float &mean, float &rstd)
 {
-    const float4 a = lds4v(stat + (uint32_t)row * 32u), b = lds4v(stat + (uint32_t)row * 32u + 16u);
-    const float s = a.x + a.z + b.x + b.z, q = a.y + a.w + b.y + b.w;
+    float4 v[NQ / 2];
+#pragma unroll
+    for (int i = 0; i < NQ / 2; ++i) v[i] = lds4v(stat + (uint32_t)row * (NQ * 8u) + 16u * i);
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NQ / 2; ++i) { s += v[i].x + v[i].z; q += v[i].y + v[i].w; }
     mean = s * inv_width;
     rstd = rsqrtf(fmaxf(q * inv_width - mean * mean, 0.f) + 1e-5f);
 }
 
 // LayerNorm(128) with affine on a fragment (bias already added); optional ReLU after.  One cta_sync inside.
-__device__ __forceinline__ void layer_norm128(float (&x)[4][4], const Thr &th, uint32_t gam, uint32_t bet, int n0, bool relu_after)
+__device__ __forceinline__ void layer_norm128(float (&x)[NT][4], const Thr &th, uint32_t gam, uint32_t bet, int n0, bool relu_after)
 {
     const uint32_t stat = sbase() + OFF_STAT;
-    stats_write<4>(x, th, stat);
+    stats_write<NT>(x, th, stat);
     cta_sync();
     float mA, sA, mB, sB;
     stats_read(stat, th.rA, 1.f / H, mA, sA);
     stats_read(stat, th.rB, 1.f / H, mB, sB);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
         const int c = n0 + 8 * nt + 2 * th.t;
         const float2 gg = ldp2(gam + 4u * c), bb = ldp2(bet + 4u * c);
         x[nt][0] = (x[nt][0] - mA) * sA * gg.x + bb.x; x[nt][1] = (x[nt][1] - mA) * sA * gg.y + bb.y;
         x[nt][2] = (x[nt][2] - mB) * sB * gg.x + bb.x; x[nt][3] = (x[nt][3] - mB) * sB * gg.y + bb.y;
     }
-    if (relu_after) relu<4>(x);
+    if (relu_after) relu<NT>(x);
 }
 
 __device__ __forceinline__ RowInfo row_info(int r)
@@ -302,6 +315,7 @@ __device__ __noinline__ void stage_gather(const Desc &d)
 {
     HSM_DECL;
     const int tid = threadIdx.x, r = tid >> 3, part = tid & 7;
+    if (tid >= TM * 8) return;
     const RowInfo ri = row_info(r);
     uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int action = -1;
@@ -329,60 +343,61 @@ __device__ __noinline__ void stage_gather(const Desc &d)
 }
 
 // x0 = relu(W_in [h | onehot] + b) + pos[agent]  -> residual fragment x, bf16 tile X
-__device__ __noinline__ void stage_inproj(const Desc &d, Ring &ring, float (&xio)[4][4])
+__device__ __noinline__ void stage_inproj(const Desc &d, Ring &ring, float (&xio)[NT][4])
 {
     const Thr th;
     const uint32_t sb = sbase();
-    const int n0 = 32 * th.nq, ldo = (d.KA + PAD) * 2;
-    float x[4][4];                  // registers (xio lives in the caller's frame: local memory)
-    zero<4>(x);
+    const int n0 = CW * th.nq, ldo = (d.KA + PAD) * 2;
+    float x[NT][4];                  // registers (xio lives in the caller's frame: local memory)
+    zero<NT>(x);
     uint32_t w = ring.acquire();
-    gemm_fixed<4, 8>(x, th, sb + OFF_HH, LDA, w, LDA, n0);
+    gemm_fixed<NT, 8>(x, th, sb + OFF_HH, LDA, w, LDA, n0);
     ring.release(th.lane);
     w = ring.acquire();
-    gemm_rt<4>(x, th, sb + OFF_ONE, LDO, w, ldo, n0, d.KA);
+    gemm_rt<NT>(x, th, sb + OFF_ONE, LDO, w, ldo, n0, d.KA);
     ring.release(th.lane);
-    add_bias<4>(x, th, sb + OFF_P + 4u * d.o_bin, n0);
+    add_bias<NT>(x, th, sb + OFF_P + 4u * d.o_bin, n0);
     const uint32_t pA = sb + OFF_P + 4u * (d.o_pos + row_info(th.rA).agent * H), pB = sb + OFF_P + 4u * (d.o_pos + row_info(th.rB).agent * H);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
         const int c = n0 + 8 * nt + 2 * th.t;
         const float2 a = ldp2(pA + 4u * c), b = ldp2(pB + 4u * c);
         x[nt][0] = fmaxf(x[nt][0], 0.f) + a.x; x[nt][1] = fmaxf(x[nt][1], 0.f) + a.y;
         x[nt][2] = fmaxf(x[nt][2], 0.f) + b.x; x[nt][3] = fmaxf(x[nt][3], 0.f) + b.y;
     }
-    store_tile<4>(sb + OFF_X, LDA, th, n0, x);
-    copy<4>(xio, x);
+    store_tile<NT>(sb + OFF_X, LDA, th, n0, x);
+    copy<NT>(xio, x);
     cta_sync();
 }
 
 // q | k | v = X W^T + b  -> bf16 rows in Q (stride LDQ).  ONE pass over the activations: the three weight chunks are
-// resident together (all ring slots), the A fragment of a k-step feeds 12 MMAs.
+// resident together (all ring slots), the A fragment of a k-step feeds 3*NT MMAs.
 __device__ __noinline__ void stage_qkv(Ring &ring, uint32_t lv)
 {
     const Thr th;
     const uint32_t sb = sbase();
-    const int n0 = 32 * th.nq;
-    float acc[12][4];
-    zero<12>(acc);
+    const int n0 = CW * th.nq;
+    float acc[3 * NT][4];
+    zero<3 * NT>(acc);
     uint32_t wa[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) wa[i] = th.w_addr(ring.acquire(i), LDA, n0);
     const uint32_t aa = th.a_addr(sb + OFF_X, LDA);
-    uint32_t a[2][4], b[2][6][4];
+    constexpr int PW = NT / 2, NP = 3 * PW;          // ldmatrix pairs of n8 tiles per weight chunk / in total
+    uint32_t a[2][4], b[2][NP][4];
     ldsm4(aa, a[0]);
 #pragma unroll
-    for (int p = 0; p < 6; ++p) ldsm4(wa[p >> 1] + (uint32_t)(16 * (p & 1)) * LDA, b[0][p]);
+    for (int p = 0; p < NP; ++p) ldsm4(wa[p / PW] + (uint32_t)(16 * (p % PW)) * LDA, b[0][p]);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
         const int cur = ks & 1, nxt = cur ^ 1;
         if (ks + 1 < 8) {
             ldsm4(aa + 32u * (ks + 1), a[nxt]);
 #pragma unroll
-            for (int p = 0; p < 6; ++p) ldsm4(wa[p >> 1] + (uint32_t)(16 * (p & 1)) * LDA + 32u * (ks + 1), b[nxt][p]);
+            for (int p = 0; p < NP; ++p) ldsm4(wa[p / PW] + (uint32_t)(16 * (p % PW)) * LDA + 32u * (ks + 1), b[nxt][p]);
         }
 #pragma unroll
-        for (int p = 0; p < 6; ++p) {
+        for (int p = 0; p < NP; ++p) {
             mma16816(acc[2 * p], a[cur], b[cur][p][0], b[cur][p][1]);
             mma16816(acc[2 * p + 1], a[cur], b[cur][p][2], b[cur][p][3]);
         }
@@ -391,10 +406,10 @@ __device__ __noinline__ void stage_qkv(Ring &ring, uint32_t lv)
 #pragma unroll
     for (int which = 0; which < 3; ++which) {
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
             const int c = n0 + 8 * nt + 2 * th.t;
             const float2 bv = ldp2(lv + 4u * (which * H + c));
-            const float *v = acc[which * 4 + nt];
+            const float *v = acc[which * NT + nt];
             sts32(sb + OFF_Q + (uint32_t)th.rA * LDQ + 2u * (which * H + c), pack2(v[0] + bv.x, v[1] + bv.y));
             sts32(sb + OFF_Q + (uint32_t)th.rB * LDQ + 2u * (which * H + c), pack2(v[2] + bv.x, v[3] + bv.y));
         }
@@ -461,6 +476,10 @@ __device__ __noinline__ void stage_attention(const Desc &d)
 {
     const uint32_t sb = sbase(), qbase = sb + OFF_Q;
     const int tid = threadIdx.x, r = tid >> 3, hh = tid & 7;
+    if (tid >= TM * NHEAD) {         // warp-uniform: (row, head) pairs fill the first 8 warps
+        cta_sync();
+        return;
+    }
     const RowInfo ri = row_info(r);
     const int N = d.N;
     float q[16], o[16];
@@ -514,20 +533,20 @@ __device__ __noinline__ void stage_attention(const Desc &d)
 }
 
 // x = LN(x + T W^T + b) * g + be   (post-LN residual block: out-proj / linear2) -> fragment x, bf16 tile X
-__device__ __noinline__ void stage_residual_ln(Ring &ring, float (&xio)[4][4], uint32_t bias, uint32_t gam, uint32_t bet)
+__device__ __noinline__ void stage_residual_ln(Ring &ring, float (&xio)[NT][4], uint32_t bias, uint32_t gam, uint32_t bet)
 {
     const Thr th;
     const uint32_t sb = sbase();
-    const int n0 = 32 * th.nq;
-    float x[4][4];                  // registers (xio lives in the caller's frame: local memory)
-    copy<4>(x, xio);
+    const int n0 = CW * th.nq;
+    float x[NT][4];                  // registers (xio lives in the caller's frame: local memory)
+    copy<NT>(x, xio);
     const uint32_t w = ring.acquire();
-    gemm_fixed<4, 8>(x, th, sb + OFF_T, LDA, w, LDA, n0);
+    gemm_fixed<NT, 8>(x, th, sb + OFF_T, LDA, w, LDA, n0);
     ring.release(th.lane);
-    add_bias<4>(x, th, bias, n0);
+    add_bias<NT>(x, th, bias, n0);
     layer_norm128(x, th, gam, bet, n0, false);
-    store_tile<4>(sb + OFF_X, LDA, th, n0, x);
-    copy<4>(xio, x);
+    store_tile<NT>(sb + OFF_X, LDA, th, n0, x);
+    copy<NT>(xio, x);
     cta_sync();
 }
 
@@ -536,15 +555,15 @@ __device__ __noinline__ void stage_linear_relu(Ring &ring, uint32_t bias)
 {
     const Thr th;
     const uint32_t sb = sbase();
-    const int n0 = 32 * th.nq;
-    float acc[4][4];
-    zero<4>(acc);
+    const int n0 = CW * th.nq;
+    float acc[NT][4];
+    zero<NT>(acc);
     const uint32_t w = ring.acquire();
-    gemm_fixed<4, 8>(acc, th, sb + OFF_X, LDA, w, LDA, n0);
+    gemm_fixed<NT, 8>(acc, th, sb + OFF_X, LDA, w, LDA, n0);
     ring.release(th.lane);
-    add_bias<4>(acc, th, bias, n0);
-    relu<4>(acc);
-    store_tile<4>(sb + OFF_T, LDA, th, n0, acc);
+    add_bias<NT>(acc, th, bias, n0);
+    relu<NT>(acc);
+    store_tile<NT>(sb + OFF_T, LDA, th, n0, acc);
     cta_sync();
 }
 
@@ -554,72 +573,72 @@ __device__ __noinline__ void stage_dynamics(const Desc &d, Ring &ring)
 {
     const Thr th;
     const uint32_t sb = sbase();
-    const int n0 = 32 * th.nq, ldo = (d.KA + PAD) * 2;
+    const int n0 = CW * th.nq, ldo = (d.KA + PAD) * 2;
     const uint32_t dv = sb + OFF_P + 4u * d.o_dyn;
-    float acc[4][4];
-    zero<4>(acc);
+    float acc[NT][4];
+    zero<NT>(acc);
     uint32_t w = ring.acquire();
-    gemm_fixed<4, 8>(acc, th, sb + OFF_HH, LDA, w, LDA, n0);        // h
+    gemm_fixed<NT, 8>(acc, th, sb + OFF_HH, LDA, w, LDA, n0);        // h
     ring.release(th.lane);
     w = ring.acquire();
-    gemm_rt<4>(acc, th, sb + OFF_ONE, LDO, w, ldo, n0, d.KA);       // one-hot action
+    gemm_rt<NT>(acc, th, sb + OFF_ONE, LDO, w, ldo, n0, d.KA);       // one-hot action
     ring.release(th.lane);
     w = ring.acquire();
-    gemm_fixed<4, 8>(acc, th, sb + OFF_X, LDA, w, LDA, n0);         // attention output
+    gemm_fixed<NT, 8>(acc, th, sb + OFF_X, LDA, w, LDA, n0);         // attention output
     ring.release(th.lane);
-    add_bias<4>(acc, th, dv, n0);
+    add_bias<NT>(acc, th, dv, n0);
     layer_norm128(acc, th, dv + 4u * 128, dv + 4u * 256, n0, true);
-    store_tile<4>(sb + OFF_T, LDA, th, n0, acc);
+    store_tile<NT>(sb + OFF_T, LDA, th, n0, acc);
     cta_sync();
-    zero<4>(acc);
+    zero<NT>(acc);
     w = ring.acquire();
-    gemm_fixed<4, 8>(acc, th, sb + OFF_T, LDA, w, LDA, n0);
+    gemm_fixed<NT, 8>(acc, th, sb + OFF_T, LDA, w, LDA, n0);
     ring.release(th.lane);
-    add_bias<4>(acc, th, dv + 4u * 384, n0);
+    add_bias<NT>(acc, th, dv + 4u * 384, n0);
     layer_norm128(acc, th, dv + 4u * 512, dv + 4u * 640, n0, true);
-    store_tile<4>(sb + OFF_X, LDA, th, n0, acc);
+    store_tile<NT>(sb + OFF_X, LDA, th, n0, acc);
     cta_sync();
     // the fp32 residual h comes straight from the pool: issue those loads before the last GEMM
     const RowInfo ra = row_info(th.rA), rb = row_info(th.rB);
-    float2 hv[2][4];
+    float2 hv[2][NT];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
         const RowInfo &ri = hf ? rb : ra;
         const int ix = (ri.valid && d.idx_x) ? __ldcg(d.idx_x + ri.root) : 0;
         const float *hp = d.pool + ((size_t)ix * d.B + (ri.valid ? ri.root : 0)) * (size_t)(d.N * H) + (size_t)ri.agent * H;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < NT; ++nt)
             hv[hf][nt] = ri.valid ? __ldcg(reinterpret_cast<const float2 *>(hp + n0 + 8 * nt + 2 * th.t)) : make_float2(0.f, 0.f);
     }
-    zero<4>(acc);
+    zero<NT>(acc);
     w = ring.acquire();
-    gemm_fixed<4, 8>(acc, th, sb + OFF_X, LDA, w, LDA, n0);
+    gemm_fixed<NT, 8>(acc, th, sb + OFF_X, LDA, w, LDA, n0);
     ring.release(th.lane);
-    add_bias<4>(acc, th, dv + 4u * 768, n0);
+    add_bias<NT>(acc, th, dv + 4u * 768, n0);
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
         const RowInfo &ri = hf ? rb : ra;
         float *nh = d.next_hidden + (size_t)(ri.valid ? ri.root : 0) * (d.N * H) + (size_t)ri.agent * H;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
             acc[nt][2 * hf] += hv[hf][nt].x;
             acc[nt][2 * hf + 1] += hv[hf][nt].y;
             if (ri.valid) *reinterpret_cast<float2 *>(nh + n0 + 8 * nt + 2 * th.t) = make_float2(acc[nt][2 * hf], acc[nt][2 * hf + 1]);
         }
     }
-    store_tile<4>(sb + OFF_T, LDA, th, n0, acc);
+    store_tile<NT>(sb + OFF_T, LDA, th, n0, acc);
     cta_sync();
 }
 
 // ---- GraphNetNN layer (model.py:151-163) in barrier phases shared by the reward and the value head --------------------
-// The stacked weight rows are interleaved on the host so that warp nq holds, for the 16 features f = 16*nq .. +15, tiles 0-1 =
-// gc.lin(x)[f] and tiles 2-3 = nn(x)[f].   y = LN(relu(sum_over_agents(gc + b_gc) + nn + b_nn)), no affine.
+// The stacked weight rows are interleaved on the host so that warp nq holds, for the FW features f = FW*nq .. +FW-1, tiles
+// [0, GT) = gc.lin(x)[f] and tiles [GT, 2*GT) = nn(x)[f].   y = LN(relu(sum_over_agents(gc + b_gc) + nn + b_nn)), no affine.
 // phase A: gc + b_gc -> G (fp32, shared);  [cta_sync]  phase B: agent sums, relu, row statistics;  [cta_sync]  phase C: normalise.
-__device__ __forceinline__ void gnn_phase_a(const float (&acc)[4][4], const Thr &th, uint32_t G, uint32_t b)
+__device__ __forceinline__ void gnn_phase_a(const float (&acc)[NT][4], const Thr &th, uint32_t G, uint32_t b)
 {
-    const int f0 = 16 * th.nq + 2 * th.t;
+    const int f0 = FW * th.nq + 2 * th.t;
 #pragma unroll
-    for (int tl = 0; tl < 2; ++tl) {
+    for (int tl = 0; tl < GT; ++tl) {
         const float2 bg = ldp2(b + 4u * (f0 + 8 * tl));
         sts2f(G + 4u * (th.rA * LDG + f0 + 8 * tl), acc[tl][0] + bg.x, acc[tl][1] + bg.y);
         sts2f(G + 4u * (th.rB * LDG + f0 + 8 * tl), acc[tl][2] + bg.x, acc[tl][3] + bg.y);
@@ -628,33 +647,34 @@ __device__ __forceinline__ void gnn_phase_a(const float (&acc)[4][4], const Thr 
 // sums over the NN agent rows of my two roots: all loads are issued before the first add (the loads are volatile and the
 // SM issues in order: a load that is consumed right away exposes its full latency)
 template <int NN>
-__device__ __forceinline__ void agent_sums(uint32_t G, int f0, int r0A, int r0B, float2 (&sa)[2], float2 (&sc)[2])
+__device__ __forceinline__ void agent_sums(uint32_t G, int f0, int r0A, int r0B, float2 (&sa)[GT], float2 (&sc)[GT])
 {
-    float2 a[NN][2], c[NN][2];
+    float2 a[NN][GT], c[NN][GT];
 #pragma unroll
     for (int j = 0; j < NN; ++j)
 #pragma unroll
-        for (int tl = 0; tl < 2; ++tl) {
+        for (int tl = 0; tl < GT; ++tl) {
             a[j][tl] = lds2f(G + 4u * ((r0A + j) * LDG + f0 + 8 * tl));
             c[j][tl] = lds2f(G + 4u * ((r0B + j) * LDG + f0 + 8 * tl));
         }
 #pragma unroll
     for (int j = 0; j < NN; ++j)
 #pragma unroll
-        for (int tl = 0; tl < 2; ++tl) {
+        for (int tl = 0; tl < GT; ++tl) {
             sa[tl].x += a[j][tl].x; sa[tl].y += a[j][tl].y; sc[tl].x += c[j][tl].x; sc[tl].y += c[j][tl].y;
         }
 }
-__device__ __forceinline__ void gnn_phase_b(const float (&acc)[4][4], const Thr &th, uint32_t G, uint32_t b, uint32_t stat, int N, int r0A,
-                                            int r0B, float (&y)[2][4])
+__device__ __forceinline__ void gnn_phase_b(const float (&acc)[NT][4], const Thr &th, uint32_t G, uint32_t b, uint32_t stat, int N, int r0A,
+                                            int r0B, float (&y)[GT][4])
 {
-    const int f0 = 16 * th.nq + 2 * th.t;
-    float2 sa[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, sc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    const int f0 = FW * th.nq + 2 * th.t;
+    float2 sa[GT], sc[GT];
+#pragma unroll
+    for (int tl = 0; tl < GT; ++tl) sa[tl] = sc[tl] = make_float2(0.f, 0.f);
     switch (N) {                       // CTA-uniform
         case 1: agent_sums<1>(G, f0, r0A, r0B, sa, sc); break;
         case 2: agent_sums<2>(G, f0, r0A, r0B, sa, sc); break;
         case 3: agent_sums<3>(G, f0, r0A, r0B, sa, sc); break;
-        case 4: agent_sums<4>(G, f0, r0A, r0B, sa, sc); break;
         default: {
             int j = 0;
 #pragma unroll 1
@@ -664,20 +684,20 @@ __device__ __forceinline__ void gnn_phase_b(const float (&acc)[4][4], const Thr 
         }
     }
 #pragma unroll
-    for (int tl = 0; tl < 2; ++tl) {
+    for (int tl = 0; tl < GT; ++tl) {
         const float2 bn = ldp2(b + 4u * (GH + f0 + 8 * tl));
-        y[tl][0] = fmaxf(sa[tl].x + acc[2 + tl][0] + bn.x, 0.f); y[tl][1] = fmaxf(sa[tl].y + acc[2 + tl][1] + bn.y, 0.f);
-        y[tl][2] = fmaxf(sc[tl].x + acc[2 + tl][2] + bn.x, 0.f); y[tl][3] = fmaxf(sc[tl].y + acc[2 + tl][3] + bn.y, 0.f);
+        y[tl][0] = fmaxf(sa[tl].x + acc[GT + tl][0] + bn.x, 0.f); y[tl][1] = fmaxf(sa[tl].y + acc[GT + tl][1] + bn.y, 0.f);
+        y[tl][2] = fmaxf(sc[tl].x + acc[GT + tl][2] + bn.x, 0.f); y[tl][3] = fmaxf(sc[tl].y + acc[GT + tl][3] + bn.y, 0.f);
     }
-    stats_write<2>(y, th, stat);
+    stats_write<GT>(y, th, stat);
 }
-__device__ __forceinline__ void gnn_phase_c(const Thr &th, uint32_t stat, float (&y)[2][4])
+__device__ __forceinline__ void gnn_phase_c(const Thr &th, uint32_t stat, float (&y)[GT][4])
 {
     float mA, sA, mB, sB;
     stats_read(stat, th.rA, 1.f / GH, mA, sA);
     stats_read(stat, th.rB, 1.f / GH, mB, sB);
 #pragma unroll
-    for (int tl = 0; tl < 2; ++tl) {
+    for (int tl = 0; tl < GT; ++tl) {
         y[tl][0] = (y[tl][0] - mA) * sA; y[tl][1] = (y[tl][1] - mA) * sA;
         y[tl][2] = (y[tl][2] - mB) * sB; y[tl][3] = (y[tl][3] - mB) * sB;
     }
@@ -689,17 +709,17 @@ __device__ __noinline__ void stage_heads1(const Desc &d, Ring &ring)
 {
     const Thr th;
     const uint32_t sb = sbase();
-    const int n0 = 32 * th.nq, ldo = (d.KA + PAD) * 2;
-    float aR[4][4], aV[4][4], aP[2][4];
-    zero<4>(aR); zero<4>(aV); zero<2>(aP);
+    const int n0 = CW * th.nq, ldo = (d.KA + PAD) * 2;
+    float aR[NT][4], aV[NT][4], aP[2][4];
+    zero<NT>(aR); zero<NT>(aV); zero<2>(aP);
     uint32_t w = ring.acquire();
-    gemm_fixed<4, 8>(aR, th, sb + OFF_T, LDA, w, LDA, n0);
+    gemm_fixed<NT, 8>(aR, th, sb + OFF_T, LDA, w, LDA, n0);
     ring.release(th.lane);
     w = ring.acquire();
-    gemm_rt<4>(aR, th, sb + OFF_ONE, LDO, w, ldo, n0, d.KA);
+    gemm_rt<NT>(aR, th, sb + OFF_ONE, LDO, w, ldo, n0, d.KA);
     ring.release(th.lane);
     w = ring.acquire();
-    gemm_fixed<4, 8>(aV, th, sb + OFF_T, LDA, w, LDA, n0);
+    gemm_fixed<NT, 8>(aV, th, sb + OFF_T, LDA, w, LDA, n0);
     ring.release(th.lane);
     w = ring.acquire();
     if (th.nq < 2) gemm_fixed<2, 8>(aP, th, sb + OFF_T, LDA, w, LDA, 16 * th.nq);   // 32 policy-hidden columns: warps nq = 0, 1
@@ -710,17 +730,17 @@ __device__ __noinline__ void stage_heads1(const Desc &d, Ring &ring)
     gnn_phase_a(aR, th, G + 4u * G_R, pr);
     gnn_phase_a(aV, th, G + 4u * G_V, pvv);
     if (th.nq < 2) add_bias<2>(aP, th, pp, 16 * th.nq);
-    stats_write<2>(aP, th, stat + 2 * TM * 32);          // (warps nq >= 2 contribute zeros)
+    stats_write<2>(aP, th, stat + 2 * STAT_SET);          // (warps nq >= 2 contribute zeros)
     cta_sync();
     // phase B
     const int r0A = row_info(th.rA).r0, r0B = row_info(th.rB).r0;
-    float yR[2][4], yV[2][4];
+    float yR[GT][4], yV[GT][4];
     gnn_phase_b(aR, th, G + 4u * G_R, pr, stat, d.N, r0A, r0B, yR);
-    gnn_phase_b(aV, th, G + 4u * G_V, pvv, stat + TM * 32, d.N, r0A, r0B, yV);
+    gnn_phase_b(aV, th, G + 4u * G_V, pvv, stat + STAT_SET, d.N, r0A, r0B, yV);
     if (th.nq < 2) {                                      // policy hidden: relu(LN(acc + b) * g + be) over 32 columns
         float mA, sA, mB, sB;
-        stats_read(stat + 2 * TM * 32, th.rA, 1.f / PH, mA, sA);
-        stats_read(stat + 2 * TM * 32, th.rB, 1.f / PH, mB, sB);
+        stats_read(stat + 2 * STAT_SET, th.rA, 1.f / PH, mA, sA);
+        stats_read(stat + 2 * STAT_SET, th.rB, 1.f / PH, mB, sB);
 #pragma unroll
         for (int tl = 0; tl < 2; ++tl) {
             const int c = 16 * th.nq + 8 * tl + 2 * th.t;
@@ -734,9 +754,9 @@ __device__ __noinline__ void stage_heads1(const Desc &d, Ring &ring)
     cta_sync();
     // phase C
     gnn_phase_c(th, stat, yR);
-    gnn_phase_c(th, stat + TM * 32, yV);
-    store_tile<2>(sb + OFF_X, LDA, th, 16 * th.nq, yR);
-    store_tile<2>(sb + OFF_X, LDA, th, GH + 16 * th.nq, yV);
+    gnn_phase_c(th, stat + STAT_SET, yV);
+    store_tile<GT>(sb + OFF_X, LDA, th, FW * th.nq, yR);
+    store_tile<GT>(sb + OFF_X, LDA, th, GH + FW * th.nq, yV);
     cta_sync();
 }
 
@@ -772,20 +792,20 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
 {
     const Thr th;
     const uint32_t sb = sbase();
-    const int n0 = 32 * th.nq, ldg = (GH + PAD) * 2;
+    const int n0 = CW * th.nq, ldg = (GH + PAD) * 2;
     const int N = d.N, A = d.A, tid = threadIdx.x;
     int hs_n = 40;
     const bool hs_on = d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0;
 #define HS() \
     if (hs_on && hs_n < 64) d.dbg_clock[hs_n++] = clock64();
     HS();
-    float aR[4][4], aV[4][4], aP[2][4];
-    zero<4>(aR); zero<4>(aV); zero<2>(aP);
+    float aR[NT][4], aV[NT][4], aP[2][4];
+    zero<NT>(aR); zero<NT>(aV); zero<2>(aP);
     uint32_t w = ring.acquire();
-    gemm_fixed<4, 4>(aR, th, sb + OFF_X, LDA, w, ldg, n0);
+    gemm_fixed<NT, 4>(aR, th, sb + OFF_X, LDA, w, ldg, n0);
     ring.release(th.lane);
     w = ring.acquire();
-    gemm_fixed<4, 4>(aV, th, sb + OFF_X + GH * 2, LDA, w, ldg, n0);
+    gemm_fixed<NT, 4>(aV, th, sb + OFF_X + GH * 2, LDA, w, ldg, n0);
     ring.release(th.lane);
     w = ring.acquire();
     const int pc0 = 16 * th.nq;                                    // policy logit columns [16*nq, +16) when < NAP
@@ -811,11 +831,11 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
     HS();
     // phase B
     const int r0A = row_info(th.rA).r0, r0B = row_info(th.rB).r0;
-    float yR[2][4], yV[2][4];
+    float yR[GT][4], yV[GT][4];
     gnn_phase_b(aR, th, G + 4u * G_R, pr, stat, N, r0A, r0B, yR);
-    gnn_phase_b(aV, th, G + 4u * G_V, pvv, stat + TM * 32, N, r0A, r0B, yV);
+    gnn_phase_b(aV, th, G + 4u * G_V, pvv, stat + STAT_SET, N, r0A, r0B, yV);
     HS();
-    {   // policy outputs: 8 threads per row (softmax, beta, greedy)
+    if (tid < TM * 8) {   // policy outputs: 8 threads per row (softmax, beta, greedy); warp-uniform condition
         const int r = tid >> 3, sub = tid & 7;
         const RowInfo ri = row_info(r);
         const uint32_t lg = PL + 4u * (r * 48);
@@ -866,10 +886,10 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
     HS();
     // phase C: normalised features (fp32) -> Y (over G, which nobody reads any more)
     gnn_phase_c(th, stat, yR);
-    gnn_phase_c(th, stat + TM * 32, yV);
+    gnn_phase_c(th, stat + STAT_SET, yV);
 #pragma unroll
-    for (int tl = 0; tl < 2; ++tl) {
-        const int f = 16 * th.nq + 8 * tl + 2 * th.t;
+    for (int tl = 0; tl < GT; ++tl) {
+        const int f = FW * th.nq + 8 * tl + 2 * th.t;
         sts2f(G + 4u * (Y_R + th.rA * GH + f), yR[tl][0], yR[tl][1]);
         sts2f(G + 4u * (Y_R + th.rB * GH + f), yR[tl][2], yR[tl][3]);
         sts2f(G + 4u * (Y_V + th.rA * GH + f), yV[tl][0], yV[tl][1]);
@@ -997,7 +1017,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_small(const
     }
     cta_sync();
     TS();
-    float x[4][4];
+    float x[NT][4];
     stage_inproj(d, ring, x);
     TS();
     const uint32_t pbase = sbase() + OFF_P;

@@ -128,6 +128,8 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
 
 // Small-batch variant (infer_hmma.cuh): 32-row tiles on warp-level MMAs.  `d->wpk` / chunk tables must be in the
 // row-major padded layout of mazero_b200/fused.py::HmmaParams.
+extern "C" int maz_infer_small_nq(void) { return hmma::NQ; }
+
 extern "C" int maz_infer_recurrent_small(const maz_infer_desc *d, void *stream)
 {
     if (!d) return set_last_error(1, "maz_infer_recurrent_small: NULL descriptor");

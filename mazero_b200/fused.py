@@ -59,10 +59,13 @@ def pack_rowmajor(w):
 
 
 def _interleave_gnn(stacked):
-    """Stacked GraphNetNN weight [gc (64 rows); nn (64 rows)] -> the column warp q of the small-batch kernel gets, in its 32
-    output columns, gc[16q:16q+16] then nn[16q:16q+16] (both halves of the 16 features it normalises)."""
+    """Stacked GraphNetNN weight [gc (64 rows); nn (64 rows)] -> column group q of the small-batch kernel gets, in its
+    128 / nq output columns, gc[fw*q : fw*(q+1)] then nn[fw*q : fw*(q+1)] (both halves of the fw = 64 / nq features it
+    normalises); nq = column groups the kernel was compiled for."""
+    nq = lib.maz_infer_small_nq()
+    fw = GH // nq
     gc, nn = stacked[:GH], stacked[GH:]
-    return torch.cat([torch.cat([gc[16 * q:16 * q + 16], nn[16 * q:16 * q + 16]]) for q in range(4)])
+    return torch.cat([torch.cat([gc[fw * q:fw * (q + 1)], nn[fw * q:fw * (q + 1)]]) for q in range(nq)])
 
 
 def _padcols(w, k):
@@ -216,7 +219,7 @@ class FusedParams:
 # Which kernel: the tcgen05 kernel needs 128-row tiles (a CTA per 4*floor(32/N) roots), the small-batch kernel 32-row tiles
 # (a CTA per floor(32/N) roots) but re-reads the 0.9 MB of weights from L2 once per CTA.  MAZ_INFER_KERNEL=small|tcgen05
 # forces one; "auto" takes the small-batch kernel while its grid stays within SMALL_MAX_TILES.
-SMALL_MAX_TILES = int(os.environ.get("MAZ_INFER_SMALL_MAX_TILES", "296"))
+SMALL_MAX_TILES = int(os.environ.get("MAZ_INFER_SMALL_MAX_TILES", "222"))   # 1.5 waves of 148 SMs (measured cross-over, profiles/prof_infer_cmp.py)
 
 
 def use_small(B, N):
