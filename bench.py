@@ -228,8 +228,11 @@ def run_ours(args):
     # ---- device-resident step: reset + prepare + S simulations (graph) + readout kernel, nothing leaves HBM
     stream = torch.cuda.current_stream(dev)
     gather = None
-    if world > 1:   # one exchange per search: root values + visit counts to every rank (learner = rank 0)
+    if world > 1 and not os.environ.get("MAZ_BENCH_NO_GATHER"):   # one exchange per search: root values + visit counts to every rank (learner = rank 0)
         gather = torch.empty(world * plan.out_flat.numel(), dtype=plan.out_flat.dtype, device=dev)
+        comm = torch.cuda.Stream(dev)                      # the exchange of search i overlaps search i+1
+        ev_ready, ev_done = torch.cuda.Event(), torch.cuda.Event()
+        ev_done.record(stream)
 
     def dev_step(seed):
         plan.tree.reset(seed, cfg.tree_value_stat_delta_lb, cfg.mcts_rho, cfg.mcts_lambda, root_off)
@@ -238,9 +241,18 @@ def run_ours(args):
             plan.graph.replay()
         else:
             plan._loop()
+        if gather is not None:
+            stream.wait_event(ev_done)                     # the previous search's readouts have been sent
         plan.tree.readout_device(cfg.discount, plan.out)
         if gather is not None:
-            dist.all_gather_into_tensor(gather, plan.out_flat)   # ONE collective per search (NCCL over NVLink)
+            # ONE collective per search (NCCL over NVLink), on its own stream: it needs every rank to arrive, so run
+            # synchronously it would add the rank skew of every 3 ms search to the step; here search i+1 hides it.
+            # Each timed step contains the wait for the previous step's exchange, so n steps account for n exchanges.
+            ev_ready.record(stream)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_ready)
+                dist.all_gather_into_tensor(gather, plan.out_flat)
+                ev_done.record(comm)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -393,7 +405,8 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}-shaped {N} agents x {A} actions, {B} roots/GPU x {S} sims, K={K}, {args.mode} mode",
                    "roots_per_gpu": B, "sims": S, "sampled_times": K, "mode": args.mode, "tree_agents": Nt,
                    "inference": inf.mode, "cuda_graph": plan.graph is not None, "l2": "flushed (256 MiB memset) between timed steps",
-                   "mean_search_depth": dbar, "mean_children": cbar, "parallelism": f"roots sharded x{world}"},
+                   "mean_search_depth": dbar, "mean_children": cbar, "parallelism": f"roots sharded x{world}",
+                   **({"exchange": "one all_gather of the packed readouts per search, overlapped with the next search"} if world > 1 else {})},
         "e2e": {"value": total_sims / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e, "api": "SampledMCTS.batch_search (host numpy + pinned hidden state)"},
         # our kernels per search: k_seed, k_prepare, k_select (first simulation), per simulation the fused inference
