@@ -208,7 +208,8 @@ def run_ours(args):
     cfg = SearchConfig(A, S, K)
     sd = random_state_dict(N, A, seed=0)
     inf = SmacInference(sd, N, A, device=dev, mode=args.inference)
-    hidden_host = root_hidden(B, N, seed=rank, pinned=True)
+    data_seed = int(os.environ.get("MAZ_BENCH_SEED", rank))      # synthetic root hidden states differ per rank
+    hidden_host = root_hidden(B, N, seed=data_seed, pinned=True)
     hidden_dev = hidden_host.to(dev)
     pol, vlog = inf.prediction(hidden_dev)
     value = inf._inv_transform(vlog, inf.vsup)
@@ -216,7 +217,7 @@ def run_ours(args):
     out_dev = out_host._replace(hidden_state=hidden_dev)
 
     mcts = SampledMCTS(cfg, np.random.RandomState(1), use_cuda_graph=not args.no_graph)
-    root_off = rank * B
+    root_off = data_seed * B
 
     def api_step(net_out):
         return mcts.batch_search(inf, net_out, cur, None, N, None, dev, add_noise=True, root_index_offset=root_off)

@@ -432,6 +432,9 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
     TreeHdr *h = f_hdr(tb);
     const size_t NA = (size_t)L.N * L.A;
     griddep_launch();
+    // profiling only (TreeLayout::dbg_clock, >= 64 + 8*B entries): per tree, cycles of expansion / backup / selection + depths
+    long long *const dbg = (L.dbg_clock && active && lane == 0) ? L.dbg_clock + 64 + (size_t)tree * 8 : nullptr;
+    const long long t0 = dbg ? clock64() : 0;
     // both warps read the header BEFORE either of them may write it
     const int tot_nodes0 = h->tot_nodes, log_len0 = h->log_len, mt_pos0 = h->mt_pos, n_exp0 = h->n_expanded, err0 = h->err;
     const int len = h->path_len;
@@ -547,9 +550,17 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
             if (err) *g_err = err;
         }
     }
+    if (dbg) dbg[role] = clock64() - t0;
     __syncthreads();   // expansion and backup of every tree of the block are complete and visible
+    const long long t2 = dbg ? clock64() : 0;
     if (active && role == 0)
         select_path_device(L, tb, h, logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
+    if (dbg && role == 0) {
+        dbg[2] = clock64() - t2;
+        dbg[3] = len;
+        dbg[4] = h->path_len;
+        dbg[5] = t2 - t0;
+    }
 }
 
 // ---- readouts (cnode.cpp:69-171, 471-530, 672-781) ------------------------------------------------------

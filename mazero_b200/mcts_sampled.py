@@ -371,10 +371,13 @@ class _DevicePlan:
 
 class SampledMCTS(object):
     def __init__(self, config, np_random: np.random.RandomState = None, use_cuda_graph: bool = True,
-                 inference_mode: str = "auto"):
+                 inference_mode: str = "auto", speculate_noise: bool = True):
         """inference_mode: "bf16" = fused tensor-core kernel, "fp32" = parity mode (plain fp32 torch ops on the
-        device), "auto" = bf16 when the network has the reference SMAC architecture, else fp32."""
+        device), "auto" = bf16 when the network has the reference SMAC architecture, else fp32.
+        speculate_noise: draw the NEXT search's exploration noise on a background thread while the GPU runs the current
+        search; it is used only if `np_random` is still in exactly the state it was left in (mazero_b200/hostrng.py)."""
         self.config = config
+        self.speculate_noise = speculate_noise
         self.np_random = np.random if np_random is None else np_random
         self.use_cuda_graph = use_cuda_graph
         self.inference_mode = inference_mode
@@ -466,6 +469,8 @@ class SampledMCTS(object):
         if sampled_actions_res is not None:
             raise NotImplementedError                                                # :108-109
         if plan is not None:
+            if self.speculate_noise:   # the next search's noise draw overlaps this search (used only if np_random is untouched)
+                hostrng.speculate(self.np_random, noise_alpha, A, B * Nt if joint else B)
             # root preparation (:57-106) runs on the device (maz_root_prepare_dev)
             r = plan.run(int(seed), cfg, noise_epsilon, noises, root_index_offset, cur=current_agent_idx)
             return _output_from_readout(r)

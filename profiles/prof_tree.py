@@ -51,7 +51,7 @@ print("mean depth", s1 / (B * sims), "nodes/tree", tot.mean())
 if os.environ.get("STAGE_CLOCKS"):
     from mazero_b200._lib import lib, check
     import ctypes as C
-    dbg = torch.zeros(64, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(64 + 8 * B, dtype=torch.int64, device=dev)
     check(lib.maz_tree_set_debug_clock(t._h, C.c_void_p(dbg.data_ptr())))
     t.expansion_backup_selection_device(sims + 1 if sims + 1 <= S else S, 0.99, K, rews[sims], vals[sims], probs[sims], probs[sims],
                                         19652.0, 1.25, ix, iy, act)
@@ -61,3 +61,13 @@ if os.environ.get("STAGE_CLOCKS"):
              2: "prefetch issued", 3: "expanded", 4: "backup done", 5: "minmax+hdr written", 6: "select done"}
     order = [0, 1, 2, 11, 12, 13, 14, 15, 3, 4, 5, 6]
     print("fused tree kernel, tree 0, cycles since start:", {names[k]: int(c[k] - c[0]) for k in order})
+    per = c[64:].reshape(B, 8)
+    exp_c, bak_c, sel_c, len_b, len_s, pre = per[:, 0], per[:, 1], per[:, 2], per[:, 3], per[:, 4], per[:, 5]
+    print("2-warp kernel, all trees: expansion cycles mean/max", exp_c.mean(), exp_c.max(), " backup mean/max", bak_c.mean(), bak_c.max(),
+          " selection mean/max", sel_c.mean(), sel_c.max(), " until barrier mean/max", pre.mean(), pre.max())
+    for d in sorted(set(len_b.tolist())):
+        m = len_b == d
+        print(f"  backup depth {d}: {m.sum()} trees, backup cycles mean {bak_c[m].mean():.0f}")
+    for d in sorted(set(len_s.tolist())):
+        m = len_s == d
+        print(f"  selection depth {d}: {m.sum()} trees, selection cycles mean {sel_c[m].mean():.0f}")

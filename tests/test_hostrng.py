@@ -68,3 +68,29 @@ def test_parallel_dirichlet_is_faster_than_numpy(built_lib):
     t_par = best(lambda: hostrng.dirichlet_f32(rs, 0.3, 9, 3072))
     print(f"numpy {t_np * 1e3:.2f} ms, parallel {t_par * 1e3:.2f} ms")
     assert t_par < t_np
+
+
+def test_speculative_draw_is_used_only_when_the_generator_is_untouched(built_lib):
+    """The background draw for the next search gives the same values / state as numpy when it is used, and is discarded
+    when anybody drew from the generator in between."""
+    from mazero_b200 import hostrng
+
+    a, b = np.random.RandomState(9), np.random.RandomState(9)
+    used0, disc0 = hostrng.STATS["used"], hostrng.STATS["discarded"]
+    for step in range(6):
+        ref = a.dirichlet([0.3] * 9, 3072).astype(np.float32)
+        got = hostrng.dirichlet_f32(b, 0.3, 9, 3072)
+        assert np.array_equal(ref, got), step
+        assert a.choice(256) == b.choice(256)
+        hostrng.speculate(b, 0.3, 9, 3072)
+        assert id(b) in hostrng._pending
+        if step % 2:                        # somebody else uses the generator between two searches (select_action ...)
+            assert a.random_sample() == b.random_sample()
+        if step == 4:                       # ... or the next search has another shape
+            ref = a.dirichlet([0.3] * 11, 1000).astype(np.float32)
+            got = hostrng.dirichlet_f32(b, 0.3, 11, 1000)
+            assert np.array_equal(ref, got)
+    assert a.random_sample() == b.random_sample()
+    sa, sb = a.get_state(), b.get_state()
+    assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+    assert hostrng.STATS["used"] - used0 == 2 and hostrng.STATS["discarded"] - disc0 == 3   # used after steps 0, 2; discarded after steps 1, 3 and for the other shape
