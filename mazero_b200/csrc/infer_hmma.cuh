@@ -1005,6 +1005,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_small(const
 #define TS() \
     if (ts_on && ts_n < 64) d.dbg_clock[ts_n++] = clock64();
     TS();
+    // PDL: everything above (and the producer warp's parameter / weight streaming, which reads constants only) may overlap the
+    // tail of the tree kernel that produces idx_x / actions; wait for it before touching its outputs or the pool.  Only then
+    // may the next tree kernel start: its pre-wait section reads tree state that the kernel we waited for was still writing.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     stage_gather(d);
     TS();
     mbar_wait(&bar_vec, 0);          // parameters resident

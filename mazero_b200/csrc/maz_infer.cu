@@ -151,8 +151,19 @@ extern "C" int maz_infer_recurrent_small(const maz_infer_desc *d, void *stream)
     }
     const int rpt = hmma::TM / d->N;
     const int tiles = (d->B + rpt - 1) / rpt;
-    hmma::k_recurrent_inference_small<<<(unsigned)tiles, hmma::NTHREADS, dyn, static_cast<cudaStream_t>(stream)>>>(*d);
-    cudaError_t e = cudaGetLastError();
+    // optionally a programmatic dependent of the tree kernel (MAZ_PDL bit 0): barrier set-up, the parameter copy and the first
+    // weight chunks overlap the predecessor's tail; the compute warps call griddepcontrol.wait before they touch its outputs
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.blockDim = dim3(hmma::NTHREADS);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (maz::pdl_mask() & 1) ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, hmma::k_recurrent_inference_small, *d);
     if (e != cudaSuccess) return set_last_error(2, std::string("k_recurrent_inference_small: ") + cudaGetErrorString(e));
     return 0;
 }
