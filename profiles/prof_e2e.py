@@ -29,29 +29,25 @@ for _ in range(20):
 pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(14)
 
-# ---- fine-grained wall-clock split of _DevicePlan.run ---------------------------------------------------------
+# ---- wall-clock split of one search (host side) ------------------------------------------------------------------
 import time
+from mazero_b200 import hostrng
 plan = next(iter(mcts._plans.values()))
-probs = np.random.rand(B, N, A).astype(np.float32); beta = probs.copy(); noises = probs.copy()
-r0 = np.zeros(B, np.float32); v0 = np.zeros(B, np.float32)
 acc = {}
 def T(name, t0):
-    torch.cuda.synchronize() if name.endswith("*") else None
     acc[name] = acc.get(name, 0.0) + (time.perf_counter() - t0)
+rs = np.random.RandomState(0)
 for it in range(20):
     torch.cuda.synchronize()
-    t = time.perf_counter(); stream = torch.cuda.current_stream(dev); plan.tree.set_stream(stream.cuda_stream); T("set_stream", t)
-    cp = lambda dst, src: dst.copy_(src if torch.is_tensor(src) else torch.from_numpy(np.ascontiguousarray(src)), non_blocking=True)
-    t = time.perf_counter(); cp(plan.pool[0], h.reshape(B, -1)); T("h2d hidden (pinned)", t)
-    t = time.perf_counter(); cp(plan.root_r, r0); cp(plan.root_v, v0); cp(plan.root_p, probs); cp(plan.root_b, beta); cp(plan.root_n, noises); T("h2d 5 small numpy", t)
-    t = time.perf_counter(); plan.tree.reset(it, 0.01, 0.75, 0.8, 0); plan.tree.prepare(plan.root_r, plan.root_v, plan.root_p, plan.root_b, K, 0.25, plan.root_n); T("reset+prepare launch", t)
-    t = time.perf_counter(); plan.graph.replay(); T("graph.replay launch", t)
-    t = time.perf_counter(); plan.tree.readout_device(0.99, plan.out); plan.out_host.copy_(plan.out_flat, non_blocking=True); T("readout launch + d2h enqueue", t)
+    t = time.perf_counter(); plan.stage_roots(out.hidden_state, out.reward, out.value, out.policy_logits, None); T("stage_roots (hidden H2D enqueue + pinned staging)", t)
+    t = time.perf_counter(); nz = hostrng.dirichlet_f32(rs, 0.3, A, B * N).reshape(B, N, A); sd = rs.choice(256); T("noise draw (parallel, bit-identical) + choice", t)
+    t = time.perf_counter(); plan._stream(); plan.inp_np["noise_raw0"][:] = nz; plan._h2d(0, plan.in_turn[0][1]); T("staging H2D enqueue", t)
+    t = time.perf_counter(); plan._enqueue_search(0, None, int(sd), cfg, 0.25, 0); T("enqueue root-prepare / reset / prepare / graph / readout", t)
+    t = time.perf_counter(); plan.out_host.copy_(plan.out_flat, non_blocking=True); T("D2H enqueue", t)
     t = time.perf_counter(); plan.tree.check(); T("check (sync = GPU time)", t)
     t = time.perf_counter(); res = {k: v.copy() for k, v in plan.out_np.items()}; T("copy out arrays", t)
-rs = np.random.RandomState(0)
 t = time.perf_counter()
 for it in range(20):
     nz = rs.dirichlet([0.3] * A, B * N).astype(np.float32)
-acc["numpy dirichlet"] = time.perf_counter() - t
+acc["(numpy dirichlet, for comparison)"] = time.perf_counter() - t
 print({k: round(v / 20 * 1e3, 3) for k, v in acc.items()}, "ms per search")
