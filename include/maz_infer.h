@@ -68,7 +68,7 @@ int maz_infer_small_nq(void);
  * `wt` is the weight TRANSPOSED to [in][out] (row-major). */
 #define MAZ_MLP_MAXLAYERS 6
 #define MAZ_MLP_MAXWIDTH 640
-enum { MAZ_MLP_LINEAR = 0, MAZ_MLP_RELU_LN = 1, MAZ_MLP_LN_RELU = 2 };
+enum { MAZ_MLP_LINEAR = 0, MAZ_MLP_RELU_LN = 1, MAZ_MLP_LN_RELU = 2, MAZ_MLP_LN_ONLY = 3 /* maz_mlp_forward only: LayerNorm of the input, no Linear */ };
 typedef struct maz_mlp_layer {
     const float *wt, *b, *ln_w, *ln_b;   /* ln_* NULL for MAZ_MLP_LINEAR */
     int in, out, kind;
@@ -96,6 +96,11 @@ typedef struct maz_mlp_desc {
 } maz_mlp_desc;
 
 int maz_mlp_recurrent(const maz_mlp_desc *desc, void *cuda_stream);
+
+/* Row-wise MLP, y[r] = net(x[r]) for `rows` independent rows: the representation network of `initial_inference`
+ * (config/smac/model.py:176-195 with its feature LayerNorm as a MAZ_MLP_LN_ONLY first layer, :470-489; config/matrix/model.py:54-83),
+ * one row per agent observation.  x (rows, net->l[0].in), y (rows, out of the last layer); fp32; device pointers. */
+int maz_mlp_forward(const maz_mlp_net *net, const float *x, int rows, float *y, void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,7 @@ SIGNATURES = {
     "maz_infer_recurrent_small": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maz_infer_small_nq": (C.c_int, []),
     "maz_mlp_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "maz_mlp_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     # include/maz_hostrng.h
     "maz_legacy_dirichlet": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     # include/maz_turn.h

@@ -272,3 +272,109 @@ extern "C" int maz_mlp_recurrent(const maz_mlp_desc *d, void *stream)
     if (e != cudaSuccess) return maz::set_last_error(2, std::string("k_mlp_recurrent: ") + cudaGetErrorString(e));
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generic row-wise MLP (the representation network of `initial_inference`: config/smac/model.py:176-195, 470-489;
+// config/matrix/model.py:54-83, 323-329): y[r] = net(x[r]) for `rows` independent rows (one agent's observation each).
+// RPC rows per CTA share every weight read; warp r normalises row r.
+namespace {
+
+constexpr int RPC = 4;     // rows per CTA (= warps per CTA)
+
+__device__ void dense_rows(const maz_mlp_layer &L, const float (*x)[MAXW], float (*y)[MAXW])
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, in = L.in, out = L.out;
+    if (L.kind != MAZ_MLP_LN_ONLY) {
+        const float *__restrict__ wt = L.wt;
+        for (int j = tid; j < out; j += NT) {
+            float acc[RPC];
+            const float b = __ldg(L.b + j);
+#pragma unroll
+            for (int r = 0; r < RPC; ++r) acc[r] = b;
+#pragma unroll 4
+            for (int i = 0; i < in; ++i) {
+                const float w = __ldg(wt + (size_t)i * out + j);
+#pragma unroll
+                for (int r = 0; r < RPC; ++r) acc[r] = fmaf(x[r][i], w, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < RPC; ++r) y[r][j] = acc[r];
+        }
+    } else {
+        for (int j = tid; j < out; j += NT)
+#pragma unroll
+            for (int r = 0; r < RPC; ++r) y[r][j] = x[r][j];
+    }
+    __syncthreads();
+    if (L.kind == MAZ_MLP_LINEAR) return;
+    // warp `warp` owns row `warp`
+    const bool relu_first = (L.kind == MAZ_MLP_RELU_LN);
+    float *row = y[warp];
+    float s = 0.f;
+    for (int j = lane; j < out; j += 32) {
+        float v = row[j];
+        if (relu_first) v = fmaxf(v, 0.f);
+        s += v;
+    }
+    const float mean = warp_sum(s) / (float)out;
+    float q = 0.f;
+    for (int j = lane; j < out; j += 32) {
+        float v = row[j];
+        if (relu_first) v = fmaxf(v, 0.f);
+        v -= mean;
+        q += v * v;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)out + 1e-5f);
+    for (int j = lane; j < out; j += 32) {
+        float v = row[j];
+        if (relu_first) v = fmaxf(v, 0.f);
+        v = (v - mean) * rstd * __ldg(L.ln_w + j) + __ldg(L.ln_b + j);
+        if (L.kind == MAZ_MLP_LN_RELU) v = fmaxf(v, 0.f);
+        row[j] = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT) k_mlp_rows(const maz_mlp_net net, const float *__restrict__ x, int rows, float *__restrict__ y)
+{
+    static_assert(NT == 32 * RPC, "one warp per row");
+    __shared__ float s_a[RPC][MAXW], s_b[RPC][MAXW];
+    const int tid = threadIdx.x, r0 = blockIdx.x * RPC;
+    const int in0 = net.l[0].in;
+    for (int r = 0; r < RPC; ++r)
+        for (int i = tid; i < in0; i += NT) s_a[r][i] = (r0 + r < rows) ? x[(size_t)(r0 + r) * in0 + i] : 0.f;
+    __syncthreads();
+    float (*src)[MAXW] = s_a, (*dst)[MAXW] = s_b;
+    for (int l = 0; l < net.n; ++l) {
+        dense_rows(net.l[l], src, dst);
+        float (*t)[MAXW] = src;
+        src = dst;
+        dst = t;
+    }
+    const int outn = net.l[net.n - 1].out;
+    for (int r = 0; r < RPC; ++r)
+        if (r0 + r < rows)
+            for (int j = tid; j < outn; j += NT) y[(size_t)(r0 + r) * outn + j] = src[r][j];
+}
+
+}   // namespace
+
+extern "C" int maz_mlp_forward(const maz_mlp_net *net, const float *x, int rows, float *y, void *stream)
+{
+    if (!net || !x || !y || rows <= 0) return maz::set_last_error(1, "maz_mlp_forward: bad arguments");
+    if (net->n < 1 || net->n > MAZ_MLP_MAXLAYERS) return maz::set_last_error(3, "maz_mlp_forward: 1..6 layers");
+    int w = net->l[0].in;
+    if (w < 1 || w > MAXW) return maz::set_last_error(3, "maz_mlp_forward: input wider than 640");
+    for (int l = 0; l < net->n; ++l) {
+        const maz_mlp_layer &L = net->l[l];
+        if (L.in != w || L.out < 1 || L.out > MAXW || L.kind < 0 || L.kind > MAZ_MLP_LN_ONLY)
+            return maz::set_last_error(3, "maz_mlp_forward: layer chain does not match");
+        if (L.kind == MAZ_MLP_LN_ONLY ? (L.in != L.out) : (!L.wt || !L.b)) return maz::set_last_error(1, "maz_mlp_forward: NULL weights");
+        if (L.kind != MAZ_MLP_LINEAR && (!L.ln_w || !L.ln_b)) return maz::set_last_error(1, "maz_mlp_forward: NULL LayerNorm affine");
+        w = L.out;
+    }
+    k_mlp_rows<<<(unsigned)((rows + RPC - 1) / RPC), NT, 0, static_cast<cudaStream_t>(stream)>>>(*net, x, rows, y);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return maz::set_last_error(2, std::string("k_mlp_rows: ") + cudaGetErrorString(e));
+    return 0;
+}

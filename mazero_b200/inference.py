@@ -103,6 +103,12 @@ class SmacInference:
                 raise RuntimeError("mode='bf16': network shape not supported by the fused kernel "
                                    "(needs the reference SMAC architecture: hidden 128, 3 layers, 8 heads, support 11)")
             self.fused = fused.FusedParams(self._params, self.N, self.A, dev)
+        # representation network (initial_inference): row-wise MLP kernel, when the state dict holds it and a GPU is there
+        self.rep = None
+        if "representation_network.mlp.0.weight" in sd and dev.type == "cuda":
+            from .inference_mlp import RowMlp
+
+            self.rep = RowMlp(sd, dev, self._params)
 
     @classmethod
     def from_model(cls, model, device="cuda", mode="fp32", **kw):
@@ -122,6 +128,18 @@ class SmacInference:
                 t.copy_(src, non_blocking=True)
         if self.fused is not None:
             self.fused.repack(self._params)
+        if self.rep is not None:
+            self.rep.retranspose()
+
+    def initial_inference(self, observation):
+        """`MAMuZeroNet.initial_inference` (config/smac/model.py:542-559) without leaving the device: observation
+        (B, N, ...) -> NetworkOutput(hidden (B, N*H), reward zeros (B,1), value (B,1), policy_logits (B,N,A)) as CUDA tensors
+        with no synchronisation (the reference's eval mode does `.cpu().numpy()` on value and logits)."""
+        if self.rep is None:
+            raise RuntimeError("the state dict holds no representation network (or no CUDA device)")
+        from .inference_mlp import initial_inference_device
+        from .synthetic import NetworkOutput
+        return NetworkOutput(*initial_inference_device(self, self.rep, observation))
 
     def recurrent_fused(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None,
                         logits_out=None, tree_agents=None, cur=-1, inv_tau=1.0, stream=None, dbg_clock=None, kernel=None):

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from ._lib import check, lib
 
 MAXL, MAXW = 6, 640
-LINEAR, RELU_LN, LN_RELU = 0, 1, 2
+LINEAR, RELU_LN, LN_RELU, LN_ONLY = 0, 1, 2, 3
 
 
 class MlpLayer(C.Structure):
@@ -104,6 +104,70 @@ class _Net:
         return self.layers[-1][0].shape[0]
 
 
+class RowMlp:
+    """The representation network of `initial_inference` (config/smac/model.py:176-195: LayerNorm of the observation, then
+    mlp(); config/matrix/model.py:54-83) as one launch of the row-wise MLP kernel (`maz_mlp_forward`), one row per agent
+    observation; `torch_forward` is the same maths in torch ops."""
+
+    def __init__(self, sd, device, registry, prefix="representation_network."):
+        self.device = torch.device(device)
+        self.net = _Net(sd, prefix + "mlp.", self.device, registry)
+        self.pre = None
+        if prefix + "feature_norm.weight" in sd:
+            g = lambda k: sd[prefix + k].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            self.pre = (g("feature_norm.weight"), g("feature_norm.bias"))
+            registry[prefix + "feature_norm.weight"], registry[prefix + "feature_norm.bias"] = self.pre
+        self.in_features = self.net.layers[0][0].shape[1]
+        self.out_features = self.net.out_features
+        if len(self.net.layers) + (self.pre is not None) > MAXL or self.in_features > MAXW:
+            raise RuntimeError("representation network not supported by the row-wise MLP kernel")
+
+    def retranspose(self):
+        self.net.retranspose()
+
+    def torch_forward(self, x):
+        if self.pre is not None:
+            x = F.layer_norm(x, [x.size(-1)], self.pre[0], self.pre[1])
+        return self.net(x)
+
+    def __call__(self, x, stream=None):
+        """x (rows, obs) fp32 CUDA tensor -> (rows, hidden)"""
+        x = x.contiguous()
+        rows = x.shape[0]
+        y = torch.empty(rows, self.out_features, dtype=torch.float32, device=self.device)
+        net = MlpNet()
+        o = 0
+        if self.pre is not None:
+            L = net.l[0]
+            L.wt = L.b = None
+            L.ln_w, L.ln_b = self.pre[0].data_ptr(), self.pre[1].data_ptr()
+            L.n_in = L.n_out = self.in_features
+            L.kind = LN_ONLY
+            o = 1
+        tmp = MlpNet()
+        self.net.fill(tmp)
+        for l in range(tmp.n):
+            for f, _ in MlpLayer._fields_:
+                setattr(net.l[o + l], f, getattr(tmp.l[l], f))
+        net.n = tmp.n + o
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        check(lib.maz_mlp_forward(C.byref(net), C.c_void_p(x.data_ptr()), int(rows), C.c_void_p(y.data_ptr()),
+                                  C.c_void_p(s.cuda_stream)))
+        return y
+
+
+def initial_inference_device(inf, rep, observation):
+    """`initial_inference` (config/smac/model.py:542-559, config/matrix/model.py:345-356) without leaving the device:
+    representation network (row-wise MLP kernel), prediction heads, inverse value transform.  Returns
+    (hidden (B, N*H), reward zeros (B, 1), value (B, 1), policy_logits (B, N, A)) as CUDA tensors, no synchronisation."""
+    B = observation.shape[0]
+    x = observation.reshape(B * inf.N, -1).to(device=inf.device, dtype=torch.float32)
+    hidden = rep(x).view(B, inf.N * inf.H)
+    pol, vlog = inf.prediction(hidden)
+    value = inf._inv_transform(vlog, inf.vsup).reshape(B, 1)
+    return hidden, torch.zeros(B, 1, dtype=torch.float32, device=inf.device), value, pol
+
+
 class MlpInference:
     """Same surface as `SmacInference` (N, A, H, device, fused, recurrent_fused, recurrent, prediction, refresh),
     so `_DevicePlan` runs the whole search of an MLP-family model on the device as well."""
@@ -136,6 +200,7 @@ class MlpInference:
         self.rsup = sup(reward_support, self.rew.out_features)
         self.vsup = sup(value_support, self.val.out_features)
         self.fused = self if mode == "fp32" else None    # `_DevicePlan` takes the one-kernel path when not None
+        self.rep = RowMlp(sd, self.device, self._params) if "representation_network.mlp.0.weight" in sd else None
 
     @classmethod
     def from_model(cls, model, device="cuda", mode="fp32", **kw):
@@ -147,8 +212,15 @@ class MlpInference:
             src = state_dict[k]
             if src.data_ptr() != t.data_ptr():
                 t.copy_(src, non_blocking=True)
-        for n in (self.dyn, self.rew, self.val, self.pol):
+        for n in (self.dyn, self.rew, self.val, self.pol) + ((self.rep,) if self.rep is not None else ()):
             n.retranspose()
+
+    def initial_inference(self, observation):
+        """observation (B, N, ...) -> NetworkOutput-like tuple of CUDA tensors (see `initial_inference_device`)."""
+        if self.rep is None:
+            raise RuntimeError("the state dict holds no representation network")
+        from .synthetic import NetworkOutput
+        return NetworkOutput(*initial_inference_device(self, self.rep, observation))
 
     # ---- one launch: gather parent hidden, recurrent_inference, inverse transforms, softmax / beta ------------
     def recurrent_fused(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None,

@@ -140,6 +140,7 @@ class _DevicePlan:
         self.in_turn = [(off[f"uniforms{t}"][0], off[f"rand_act{t}"][1]) for t in range(T)]
         self.root_r, self.root_v = self.inp["rewards"], self.inp["values"]
         self.has_legal = False
+        self._dev_fields = []
         # ---- device -> host: all readouts of all turns + the turn results in ONE buffer / ONE D2H copy -------------
         spec = [("value", f32, (B,)), ("marginal_visit_count", i32, (B, self.Nt, self.A)),
                 ("marginal_priors", f32, (B, self.Nt, self.A)), ("num_children", i32, (B,)),
@@ -264,14 +265,26 @@ class _DevicePlan:
         B, h = self.B, self.inp_np
         src = root_hidden if torch.is_tensor(root_hidden) else torch.from_numpy(np.ascontiguousarray(root_hidden))
         self.pool[0].copy_(src.reshape(B, -1), non_blocking=True)
-        h["rewards"][:] = np.asarray(rewards).reshape(B)
-        h["values"][:] = np.asarray(values).reshape(B)
-        h["logits"][:] = np.asarray(logits).reshape(B, self.N, self.A)
+        self._dev_fields = []      # inputs that already live on the device: copied over the staging block after its H2D
+
+        def put(name, x, shape):
+            if torch.is_tensor(x) and x.is_cuda:
+                self._dev_fields.append((name, x.detach().reshape(shape)))
+            else:
+                h[name][:] = (x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)).reshape(shape)
+
+        put("rewards", rewards, (B,))
+        put("values", values, (B,))
+        put("logits", logits, (B, self.N, self.A))
         self.has_legal = legal is not None
         if legal is not None:
-            h["legal"][:] = np.asarray(legal).reshape(B, self.N, self.A)
+            put("legal", legal, (B, self.N, self.A))
         if factor is not None and cur:
-            h["factor_in"][:, :cur] = np.asarray(factor)[:, :cur]
+            h["factor_in"][:, :cur] = (factor.detach().cpu().numpy() if torch.is_tensor(factor) else np.asarray(factor))[:, :cur]
+
+    def _apply_dev_fields(self):
+        for name, t in self._dev_fields:
+            self.inp[name].copy_(t, non_blocking=True)
 
     def _h2d(self, a, b):
         self.in_flat[a:b].copy_(self.in_host[a:b], non_blocking=True)
@@ -309,6 +322,7 @@ class _DevicePlan:
         self._stream()
         self.inp_np["noise_raw0"][:] = noise_raw
         self._h2d(0, self.in_turn[0][1])
+        self._apply_dev_fields()
         if cur:
             self.factor[:, :cur].copy_(self.inp["factor_in"][:, :cur], non_blocking=True)
         self._enqueue_search(0, cur, seed, cfg, noise_eps, root_index_offset)
@@ -320,6 +334,7 @@ class _DevicePlan:
     def begin_turns(self):
         self._stream()
         self._h2d(*self.in_common)
+        self._apply_dev_fields()
 
     def enqueue_turn(self, k, mode, seed, cfg, noise_eps, noise_raw, inv_temperature=1.0, uniforms=None, greedy_epsilon=0.0,
                      eps_u=None, rand_act=None, root_index_offset=0):
@@ -448,9 +463,6 @@ class SampledMCTS(object):
         def host(x):
             return x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
 
-        batch_rewards, batch_values = host(network_output.reward), host(network_output.value)
-        all_logits = host(network_output.policy_logits)
-        assert batch_values.shape == (B, 1) and all_logits.size == B * true_num_agents * A
         if not add_noise:
             noise_epsilon = 0.0
 
@@ -458,9 +470,14 @@ class SampledMCTS(object):
         plan = None
         if inf is not None:
             plan = self._plan(inf, B, current_agent_idx, sampled_tau)
-            # the copies that do not depend on the host RNG are in flight while numpy draws the noise
-            plan.stage_roots(network_output.hidden_state, batch_rewards, batch_values, all_logits, legal_actions_lst, factor,
-                             current_agent_idx)
+            # the copies that do not depend on the host RNG are in flight while the noise is drawn; reward / value / logits may
+            # be numpy (the reference's eval-mode NetworkOutput) or CUDA tensors (`inf.initial_inference`: nothing leaves the GPU)
+            plan.stage_roots(network_output.hidden_state, network_output.reward, network_output.value, network_output.policy_logits,
+                             legal_actions_lst, factor, current_agent_idx)
+        else:
+            batch_rewards, batch_values = host(network_output.reward), host(network_output.value)
+            all_logits = host(network_output.policy_logits)
+            assert batch_values.shape == (B, 1) and all_logits.size == B * true_num_agents * A
 
         # exploration noise (:68-70): drawn even when add_noise is False, one Dirichlet per (root, tree agent)
         # (hostrng: the same values and the same final generator state as np_random.dirichlet, on all host cores)
@@ -542,8 +559,8 @@ class SampledMCTS(object):
         host = lambda x: x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
         noise_epsilon = cfg.root_exploration_fraction if add_noise else 0.0
         plan = self._plan(inf, B, 0, sampled_tau)
-        plan.stage_roots(network_output.hidden_state, host(network_output.reward), host(network_output.value),
-                         host(network_output.policy_logits), legal_actions_lst)
+        plan.stage_roots(network_output.hidden_state, network_output.reward, network_output.value,
+                         network_output.policy_logits, legal_actions_lst)
         plan.begin_turns()
         eps_u, rand_act = (None, None) if eps_randoms is None else eps_randoms
         for k in range(N):

@@ -97,6 +97,16 @@ class _Prediction(nn.Module):  # config/smac/model.py:285-373
         self.fc_policy = _mlp([h] + list(pol_layers) + [a])
 
 
+class _Representation(nn.Module):  # config/smac/model.py:176-195 (use_feature_norm=True)
+    def __init__(self, obs, h, layers):
+        super().__init__()
+        self.feature_norm = nn.LayerNorm(obs)
+        self.mlp = _mlp([obs] + list(layers) + [h])
+
+    def forward(self, x):
+        return self.mlp(self.feature_norm(x))
+
+
 def inverse_support_transform(logits, support_min, support_max):
     """softmax . support -> inv_h   (core/config.py:430-442, 463-475, 494-499)"""
     eps = 0.001
@@ -117,8 +127,12 @@ class OracleMAMuZeroNet(nn.Module):
     by `load_reference_state_dict`."""
 
     def __init__(self, num_agents, action_space_size, hidden_state_size=128, fc_dynamic_layers=(128, 128),
-                 fc_policy_layers=(32,), reward_support=(-5, 5), value_support=(-5, 5), gnn_hidden=64):
+                 fc_policy_layers=(32,), reward_support=(-5, 5), value_support=(-5, 5), gnn_hidden=64, obs_size=None,
+                 fc_representation_layers=None):
         super().__init__()
+        if obs_size is not None:   # representation network (config/smac/model.py:176-195), only for initial_inference
+            rl = list(fc_representation_layers if fc_representation_layers is not None else (hidden_state_size, hidden_state_size))
+            self.representation_network = _Representation(obs_size, hidden_state_size, rl)
         self.num_agents, self.action_space_size, self.hidden = num_agents, action_space_size, hidden_state_size
         self.reward_support, self.value_support = reward_support, value_support
         rs = reward_support[1] - reward_support[0] + 1
@@ -150,6 +164,14 @@ class OracleMAMuZeroNet(nn.Module):
             head.weight.data.copy_((torch.rand(head.weight.shape, generator=g) * 2 - 1) * scale)
             head.bias.data.zero_()
         return self
+
+    @torch.no_grad()
+    def initial_inference(self, observation):
+        """config/smac/model.py:470-489, 542-559: (hidden (B,N*H), value (B,1), policy_logits (B,N,A))"""
+        b = observation.shape[0]
+        hidden = self.representation_network(observation.reshape(b * self.num_agents, -1)).reshape(b, -1)
+        pol, vlog = self.prediction(hidden)
+        return hidden, inverse_support_transform(vlog, *self.value_support), pol
 
     # -- the two methods the search calls ---------------------------------------------------------------
     def prediction(self, hidden):
@@ -210,8 +232,11 @@ class OracleMatrixMuZeroNet(nn.Module):
 
     def __init__(self, num_agents=2, action_space_size=3, hidden_state_size=64, fc_dynamic_layers=(64, 64),
                  fc_reward_layers=(32,), fc_value_layers=(32,), fc_policy_layers=(32,), reward_support=(-3, 3),
-                 value_support=(-10, 10)):
+                 value_support=(-10, 10), obs_size=None, fc_representation_layers=(64, 64)):
         super().__init__()
+        if obs_size is not None:   # representation network (config/matrix/model.py:54-83, use_feature_norm=False)
+            self.representation_network = nn.Module()
+            self.representation_network.mlp = _matrix_mlp([obs_size] + list(fc_representation_layers) + [hidden_state_size])
         self.num_agents, self.action_space_size, self.hidden_state_size = num_agents, action_space_size, hidden_state_size
         self.hidden = hidden_state_size
         self.reward_support, self.value_support = tuple(reward_support), tuple(value_support)
@@ -232,6 +257,13 @@ class OracleMatrixMuZeroNet(nn.Module):
                 m.weight.data.copy_(w)
                 m.bias.data.zero_()
         return self
+
+    @torch.no_grad()
+    def initial_inference(self, observation):  # config/matrix/model.py:323-329, 345-356
+        b = observation.shape[0]
+        hidden = self.representation_network.mlp(observation.reshape(b * self.num_agents, -1)).reshape(b, -1)
+        pol, v = self.prediction(hidden)
+        return hidden, self._inv(v, self.value_support), pol
 
     def prediction(self, hidden):  # config/matrix/model.py:163-166, 320-322
         b = hidden.shape[0]

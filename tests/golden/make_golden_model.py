@@ -106,14 +106,18 @@ def main_matrix():
         g = torch.Generator().manual_seed(2)
         hidden = torch.randn(b, n * h, generator=g)
         action = torch.randint(0, a, (b, n), generator=g)
+        obs = torch.randn(b, n, 4, generator=g)
         with torch.no_grad():
             pol, vlog = m.prediction(hidden)
             out = m.recurrent_inference(hidden, action)
+            ini = m.initial_inference(obs)
         keep = {k: v.numpy() for k, v in m.state_dict().items()
-                if k.startswith(("dynamics_network.", "prediction_network."))}
+                if k.startswith(("dynamics_network.", "prediction_network.", "representation_network."))}
         path = os.path.join(HERE, f"model_{name}.npz")
         np.savez_compressed(
             path, dims=np.array([n, a, h, b], dtype=np.int32), hidden=hidden.numpy(), action=action.numpy().astype(np.int32),
+            obs=obs.numpy(), init_hidden=ini.hidden_state.numpy(), init_value=np.asarray(ini.value, dtype=np.float32),
+            init_policy_logits=np.asarray(ini.policy_logits, dtype=np.float32),
             supports=np.array([cfg.reward_support.min, cfg.reward_support.max, cfg.value_support.min, cfg.value_support.max],
                               dtype=np.int32),
             pred_policy_logits=pol.numpy(), pred_value_logits=vlog.numpy(),
@@ -131,14 +135,18 @@ def main():
         g = torch.Generator().manual_seed(2)
         hidden = torch.randn(b, n * h, generator=g)
         action = torch.randint(0, a, (b, n), generator=g)
+        obs = torch.randn(b, n, 16, 1, 1, generator=g)
         with torch.no_grad():
             pol, vlog = m.prediction(hidden)
             out = m.recurrent_inference(hidden, action)
+            ini = m.initial_inference(obs)
         keep = {k: v.numpy() for k, v in m.state_dict().items()
-                if k.startswith(("dynamics_network.", "prediction_network."))}
+                if k.startswith(("dynamics_network.", "prediction_network.", "representation_network."))}
         path = os.path.join(HERE, f"model_{name}.npz")
         np.savez_compressed(
             path, dims=np.array([n, a, h, b], dtype=np.int32), hidden=hidden.numpy(), action=action.numpy().astype(np.int32),
+            obs=obs.numpy(), init_hidden=ini.hidden_state.numpy(), init_value=np.asarray(ini.value, dtype=np.float32),
+            init_policy_logits=np.asarray(ini.policy_logits, dtype=np.float32),
             pred_policy_logits=pol.numpy(), pred_value_logits=vlog.numpy(),
             rec_hidden=out.hidden_state.numpy(), rec_reward=np.asarray(out.reward, dtype=np.float32),
             rec_value=np.asarray(out.value, dtype=np.float32), rec_policy_logits=np.asarray(out.policy_logits, dtype=np.float32),

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from test_model_oracle import MODEL_GOLDEN, load_model_golden
+from test_model_oracle import MODEL_GOLDEN, load_model_golden  # noqa: E402
 from test_search_gpu import device_path_replay
 
 pytestmark = pytest.mark.gpu
@@ -102,3 +102,39 @@ def test_reference_style_matrix_module_is_adapted(built_lib):
     o = mcts.batch_search(net, out0, None, None, n, None, torch.device("cuda:0"), add_noise=True)
     assert isinstance(next(iter(mcts._inference.values())), MlpInference) and len(mcts._plans) == 1
     assert (o.marginal_visit_count.sum(axis=2) == S).all()
+
+
+@pytest.mark.parametrize("path", MODEL_GOLDEN, ids=[p.split("model_")[-1][:-4] for p in MODEL_GOLDEN])
+def test_initial_inference_on_device_matches_reference_network(built_lib, path):
+    """`initial_inference` without leaving the GPU (row-wise MLP kernel for the representation network + prediction heads +
+    inverse value transform) against the REAL reference networks' outputs, SMAC and matrix families; and a search started
+    from those device tensors equals the search started from the same values as host arrays."""
+    from mazero_b200.inference import SmacInference
+    from mazero_b200.mcts_sampled import SampledMCTS
+    from oracle.search_oracle import NetworkOutput
+    from _mock import MockConfig
+
+    z, _, sd, (n, a, h, b) = load_model_golden(path)
+    tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+    if "supports" in z.files:
+        inf = _inference(z, sd, n, a, h)
+    else:
+        inf = SmacInference(tsd, n, a, h, device="cuda:0", mode="fp32")
+    obs = torch.from_numpy(z["obs"]).cuda()
+    out = inf.initial_inference(obs)
+    assert all(t.is_cuda for t in (out.hidden_state, out.reward, out.value, out.policy_logits))
+    tol = dict(rtol=1e-5, atol=3e-6)
+    np.testing.assert_allclose(out.hidden_state.cpu().numpy(), z["init_hidden"], **tol)
+    np.testing.assert_allclose(out.policy_logits.cpu().numpy(), z["init_policy_logits"], **tol)
+    np.testing.assert_allclose(out.value.cpu().numpy().reshape(-1), z["init_value"].reshape(-1), rtol=1e-4, atol=1e-5)
+    # kernel == its torch twin
+    x = obs.reshape(b * n, -1).float()
+    np.testing.assert_allclose(inf.rep(x).cpu().numpy(), inf.rep.torch_forward(x).cpu().numpy(), **tol)
+    # search from device tensors == search from the same values on the host
+    cfg = MockConfig(n, a, 12, 5)
+    dev_res = SampledMCTS(cfg, np.random.RandomState(4)).batch_search(inf, out, 0, None, n, None, "cuda:0", add_noise=True)
+    host_out = NetworkOutput(out.hidden_state, out.reward.cpu().numpy(), out.value.cpu().numpy(), out.policy_logits.cpu().numpy())
+    host_res = SampledMCTS(cfg, np.random.RandomState(4)).batch_search(inf, host_out, 0, None, n, None, "cuda:0", add_noise=True)
+    for f in dev_res._fields:
+        x, y = getattr(dev_res, f), getattr(host_res, f)
+        assert np.array_equal(x, y) if isinstance(y, np.ndarray) else x == y, f
