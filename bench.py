@@ -31,6 +31,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_JSON_FD = None     # set when fd 1 has been redirected (multi-rank runs)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 METRIC = "mcts_sims_per_sec"
 UNIT = "root-sims/s"
 
@@ -200,6 +212,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL printf()s its version banner to fd 1 at communicator creation, so fd 1 is
+        # pointed at stderr for the whole run and the JSON line goes to a saved copy of the original stdout
+        sys.stdout.flush()
+        global _JSON_FD
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     N, A, B, S, K = workload(args)
@@ -208,23 +226,38 @@ def run_ours(args):
     cfg = SearchConfig(A, S, K)
     sd = random_state_dict(N, A, seed=0)
     inf = SmacInference(sd, N, A, device=dev, mode=args.inference)
-    data_seed = int(os.environ.get("MAZ_BENCH_SEED", rank))      # synthetic root hidden states differ per rank
-    hidden_host = root_hidden(B, N, seed=data_seed, pinned=True)
-    hidden_dev = hidden_host.to(dev)
-    pol, vlog = inf.prediction(hidden_dev)
-    value = inf._inv_transform(vlog, inf.vsup)
-    out_host = NetworkOutput(hidden_host, np.zeros((B, 1), np.float32), value.cpu().numpy().reshape(B, 1), pol.cpu().numpy())
-    out_dev = out_host._replace(hidden_state=hidden_dev)
-
+    # Synthetic inputs: NSETS different batches of root hidden states, rotated per step with a rank offset.  The search time
+    # depends on the inputs (the tree step ends with the deepest of the 1024 trees: 3.3 - 3.6 ms across batches), so one fixed
+    # batch would make the single-GPU number a draw from that range and the max-over-ranks of a multi-GPU run a maximum of
+    # such draws; with the rotation every rank does the same work on average, whatever the number of ranks.
+    NSETS = int(os.environ.get("MAZ_BENCH_INPUT_SETS", "5"))
+    base_seed = int(os.environ.get("MAZ_BENCH_SEED", "0"))
+    root_off = rank * B                              # global root index of this rank's first root (tree RNG seeding)
     mcts = SampledMCTS(cfg, np.random.RandomState(1), use_cuda_graph=not args.no_graph)
-    root_off = data_seed * B
 
     def api_step(net_out):
         return mcts.batch_search(inf, net_out, cur, None, N, None, dev, add_noise=True, root_index_offset=root_off)
 
-    first = api_step(out_dev)                       # builds the plan + captures the CUDA graph
-    plan = next(iter(mcts._plans.values()))
-    assert int(first.marginal_visit_count[0, 0].sum()) == S
+    outs_host, outs_dev, snaps = [], [], []
+    plan = None
+    for k in range(NSETS):
+        hidden_host = root_hidden(B, N, seed=base_seed + k, pinned=True)
+        hidden_dev = hidden_host.to(dev)
+        pol, vlog = inf.prediction(hidden_dev)
+        value = inf._inv_transform(vlog, inf.vsup)
+        oh = NetworkOutput(hidden_host, np.zeros((B, 1), np.float32), value.cpu().numpy().reshape(B, 1), pol.cpu().numpy())
+        outs_host.append(oh)
+        outs_dev.append(oh._replace(hidden_state=hidden_dev))
+        first = api_step(outs_dev[-1])               # (k = 0: builds the plan + captures the CUDA graph)
+        assert int(first.marginal_visit_count[0, 0].sum()) == S
+        plan = next(iter(mcts._plans.values()))
+        # device-resident copy of this batch's prepared roots: hidden state + the arrays Tree_batch.prepare takes
+        snaps.append([t.clone() for t in (plan.pool[0], plan.root_r, plan.root_v, plan.root_p, plan.root_b, plan.root_n)])
+    hidden_host = outs_host[0].hidden_state
+
+    def load_set(k):
+        for dst, src in zip((plan.pool[0], plan.root_r, plan.root_v, plan.root_p, plan.root_b, plan.root_n), snaps[k]):
+            dst.copy_(src, non_blocking=True)
 
     # ---- device-resident step: reset + prepare + S simulations (graph) + readout kernel, nothing leaves HBM
     stream = torch.cuda.current_stream(dev)
@@ -236,6 +269,7 @@ def run_ours(args):
         ev_done.record(stream)
 
     def dev_step(seed):
+        load_set((seed + rank) % NSETS)                    # 1.6 MB of device-to-device copies, inside the timed step
         plan.tree.reset(seed, cfg.tree_value_stat_delta_lb, cfg.mcts_rho, cfg.mcts_lambda, root_off)
         plan.tree.prepare(plan.root_r, plan.root_v, plan.root_p, plan.root_b, K, cfg.root_exploration_fraction, plan.root_n)
         if plan.graph is not None:
@@ -290,7 +324,7 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers (pinned hidden state, numpy everything else)
     def e2e_step(i):
-        api_step(out_host)
+        api_step(outs_host[(i + rank) % NSETS])
 
     # batch_search synchronises internally (it returns numpy); wall-clock == device time here, but keep events
     ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
@@ -305,12 +339,12 @@ def run_ours(args):
         def loop_step(i):
             acts = np.zeros((B, N), dtype=np.int32)
             for k in range(N):
-                o = mcts.batch_search(inf, out_host, k, acts[:, :k].copy() if k else None, N, None, dev, add_noise=True,
+                o = mcts.batch_search(inf, outs_host[(i + rank) % NSETS], k, acts[:, :k].copy() if k else None, N, None, dev, add_noise=True,
                                       root_index_offset=root_off)
                 acts[:, k] = np.argmax(o.marginal_visit_count[:, 0, :], axis=-1)      # reanalyze_worker.py:309
 
         def fused_step(i):
-            mcts.search_agents(inf, out_host, N, None, dev, add_noise=True, turn="greedy", root_index_offset=root_off)
+            mcts.search_agents(inf, outs_host[(i + rank) % NSETS], N, None, dev, add_noise=True, turn="greedy", root_index_offset=root_off)
 
         fused_step(0)
         ms_loop = timed(loop_step, args.steps, max(args.warmup, 3))
@@ -406,6 +440,7 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}-shaped {N} agents x {A} actions, {B} roots/GPU x {S} sims, K={K}, {args.mode} mode",
                    "roots_per_gpu": B, "sims": S, "sampled_times": K, "mode": args.mode, "tree_agents": Nt,
                    "inference": inf.mode, "cuda_graph": plan.graph is not None, "l2": "flushed (256 MiB memset) between timed steps",
+                   "inputs": f"{NSETS} synthetic batches of root hidden states rotated per step (rank offset)",
                    "mean_search_depth": dbar, "mean_children": cbar, "parallelism": f"roots sharded x{world}",
                    **({"exchange": "one all_gather of the packed readouts per search, overlapped with the next search"} if world > 1 else {})},
         "e2e": {"value": total_sims / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -426,7 +461,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": Bs * S / sec, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"{Bs} roots x {S} sims, 2 timed searches after 1 warm-up; reference C++ tree "
                                           f"({kind}) single-threaded + torch CPU {cores} threads"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
