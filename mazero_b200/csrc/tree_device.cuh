@@ -409,6 +409,8 @@ __device__ __forceinline__ void vs_apply(const TreeLayout &L, char *tb, int &log
 
     bool append_big;
     int flip_pos = -1;       // log entry whose big/small flag flips
+    uint32_t flip_key = 0;   // its new key: an entry of this set is exactly tag | flag, so the flip is a plain store (a
+                             // read-modify-write of the log in global memory would stall the warp for an L2 round trip per level)
     if (nbig == lim) {       // utils.cpp:33-48
         const uint32_t gmin = __reduce_min_sync(MAZ_FULL, r.minpos >= 0 ? r.minbig : 0xffffffffu);
         const float m = ord2f(gmin);
@@ -417,6 +419,7 @@ __device__ __forceinline__ void vs_apply(const TreeLayout &L, char *tb, int &log
         } else {
             const unsigned who = __ballot_sync(MAZ_FULL, r.minpos >= 0 && r.minbig == gmin);
             flip_pos = __shfl_sync(MAZ_FULL, r.minpos, __ffs(who) - 1);
+            flip_key = tag;                       // min(big) moves to the small set
             wsum = __fsub_rn(wsum, __fmul_rn(lp, m));
             wtot = __fsub_rn(wtot, lp);
             append_big = true;
@@ -439,6 +442,7 @@ __device__ __forceinline__ void vs_apply(const TreeLayout &L, char *tb, int &log
             } else {
                 const unsigned who = __ballot_sync(MAZ_FULL, r.maxpos >= 0 && r.maxsmall == gmax);
                 flip_pos = __shfl_sync(MAZ_FULL, r.maxpos, __ffs(who) - 1);
+                flip_key = tag | 1u;              // max(small) moves to the big set
                 wtot = __fadd_rn(wtot, lp);
                 wsum = __fadd_rn(wsum, __fmul_rn(lp, M));
                 append_big = false;
@@ -450,7 +454,7 @@ __device__ __forceinline__ void vs_apply(const TreeLayout &L, char *tb, int &log
         return;
     }
     if (lane == 0) {
-        if (flip_pos >= 0) vk[flip_pos] ^= 1u;
+        if (flip_pos >= 0) vk[flip_pos] = flip_key;
         vk[log_len] = tag | (append_big ? 1u : 0u);
         vv[log_len] = key;
     }
