@@ -112,20 +112,11 @@ static int build_layout(TreeLayout &L, int B, int N, int A, int K, int S, float 
     unsigned long long o = sizeof(TreeHdr);
     auto take = [&](unsigned long long bytes) { o = align_up(o, 128); unsigned at = (unsigned)o; o += bytes; return at; };
     L.off_mt = take(4ull * kMtN);
-    L.off_prior = take(4ull * Pp);
+    L.off_rec = take(sizeof(NodeRec) * Pp);
     L.off_pred_prob = take(4ull * Pp);
     L.off_beta = take(4ull * Pp);
     L.off_beta_hat = take(4ull * Pp);
-    L.off_reward = take(4ull * Pp);
-    L.off_pred_value = take(4ull * Pp);
-    L.off_wsum = take(4ull * Pp);
-    L.off_wtot = take(4ull * Pp);
     L.off_qdelta = take(4ull * Pp);
-    L.off_visit = take(4ull * Pp);
-    L.off_nchild = take(2ull * Pp);
-    L.off_cbase = take(2ull * Pp);
-    L.off_hidx = take(2ull * Pp);
-    L.off_eid = take(2ull * Pp);
     L.off_actions = take(1ull * Pp * N);
     L.off_expslot = take(2ull * (S + 4));
     L.off_path = take(2ull * (S + 4));

@@ -13,6 +13,8 @@
 
 #include "tree_layout.h"
 
+#include <cstddef>
+
 namespace maz {
 
 #define MAZ_FULL 0xffffffffu
@@ -21,26 +23,68 @@ namespace maz {
 #define MAZ_FIELD(type, name, off)                                                                      \
     __device__ __forceinline__ type *name(const TreeLayout &L, char *tb) { return reinterpret_cast<type *>(tb + L.off); }
 MAZ_FIELD(uint32_t, f_mt, off_mt)
-MAZ_FIELD(float, f_prior, off_prior)
+MAZ_FIELD(NodeRec, f_rec, off_rec)
 MAZ_FIELD(float, f_pred_prob, off_pred_prob)
 MAZ_FIELD(float, f_beta, off_beta)
 MAZ_FIELD(float, f_beta_hat, off_beta_hat)
-MAZ_FIELD(float, f_reward, off_reward)
-MAZ_FIELD(float, f_pred_value, off_pred_value)
-MAZ_FIELD(float, f_wsum, off_wsum)
-MAZ_FIELD(float, f_wtot, off_wtot)
 MAZ_FIELD(float, f_qdelta, off_qdelta)
-MAZ_FIELD(int, f_visit, off_visit)
-MAZ_FIELD(uint16_t, f_nchild, off_nchild)
-MAZ_FIELD(uint16_t, f_cbase, off_cbase)
-MAZ_FIELD(int16_t, f_hidx, off_hidx)
-MAZ_FIELD(uint16_t, f_eid, off_eid)
 MAZ_FIELD(uint8_t, f_actions, off_actions)
 MAZ_FIELD(uint16_t, f_expslot, off_expslot)
 MAZ_FIELD(uint16_t, f_path, off_path)
 MAZ_FIELD(uint32_t, f_vskey, off_vskey)
 MAZ_FIELD(float, f_vsval, off_vsval)
 #undef MAZ_FIELD
+
+// one field of the node records, indexed by slot (the cold paths keep the array notation; the hot paths load whole records)
+template <typename T, size_t OFF>
+struct RecField {
+    char *base;
+    __device__ __forceinline__ T &operator[](int slot) const { return *reinterpret_cast<T *>(base + (size_t)slot * sizeof(NodeRec) + OFF); }
+};
+#define MAZ_RECFIELD(type, name, member)                                                    \
+    __device__ __forceinline__ RecField<type, offsetof(NodeRec, member)> name(const TreeLayout &L, char *tb) \
+    {                                                                                       \
+        return RecField<type, offsetof(NodeRec, member)>{tb + L.off_rec};                   \
+    }
+MAZ_RECFIELD(float, f_prior, prior)
+MAZ_RECFIELD(float, f_reward, reward)
+MAZ_RECFIELD(float, f_pred_value, pred_value)
+MAZ_RECFIELD(float, f_wsum, wsum)
+MAZ_RECFIELD(float, f_wtot, wtot)
+MAZ_RECFIELD(int, f_visit, visit)
+MAZ_RECFIELD(uint16_t, f_nchild, nchild)
+MAZ_RECFIELD(uint16_t, f_cbase, cbase)
+MAZ_RECFIELD(int16_t, f_hidx, hidx)
+MAZ_RECFIELD(uint16_t, f_eid, eid)
+#undef MAZ_RECFIELD
+
+// whole-record access: two 16-byte transactions
+struct RecRegs { uint4 a, b; };
+__device__ __forceinline__ RecRegs rec_load(const TreeLayout &L, char *tb, int slot)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(tb + L.off_rec + (size_t)slot * sizeof(NodeRec));
+    RecRegs r;
+    r.a = p[0];
+    r.b = p[1];
+    return r;
+}
+__device__ __forceinline__ float rec_prior(const RecRegs &r) { return __uint_as_float(r.a.x); }
+__device__ __forceinline__ float rec_reward(const RecRegs &r) { return __uint_as_float(r.a.y); }
+__device__ __forceinline__ float rec_pred_value(const RecRegs &r) { return __uint_as_float(r.a.z); }
+__device__ __forceinline__ float rec_wsum(const RecRegs &r) { return __uint_as_float(r.a.w); }
+__device__ __forceinline__ float rec_wtot(const RecRegs &r) { return __uint_as_float(r.b.x); }
+__device__ __forceinline__ int rec_visit(const RecRegs &r) { return (int)r.b.y; }
+__device__ __forceinline__ int rec_nchild(const RecRegs &r) { return (int)(r.b.z & 0xffffu); }
+__device__ __forceinline__ int rec_cbase(const RecRegs &r) { return (int)(r.b.z >> 16); }
+__device__ __forceinline__ int rec_hidx(const RecRegs &r) { return (int)(int16_t)(r.b.w & 0xffffu); }
+__device__ __forceinline__ int rec_eid(const RecRegs &r) { return (int)(r.b.w >> 16); }
+// a freshly created child (CNode ctor, cnode.cpp:14-16): prior set, everything else zero, hidden index -1
+__device__ __forceinline__ void rec_store_new_child(const TreeLayout &L, char *tb, int slot, float prior)
+{
+    uint4 *p = reinterpret_cast<uint4 *>(tb + L.off_rec + (size_t)slot * sizeof(NodeRec));
+    p[0] = make_uint4(__float_as_uint(prior), 0u, 0u, 0u);      // prior, reward 0, pred_value 0, wsum 0
+    p[1] = make_uint4(0u, 0u, 0u, 0x0000ffffu);                  // wtot 0, visit 0, nchild 0 | cbase 0, hidx -1 | eid 0
+}
 
 __device__ __forceinline__ TreeHdr *f_hdr(char *tb) { return reinterpret_cast<TreeHdr *>(tb); }
 
@@ -338,15 +382,10 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
             act[i] = (uint8_t)a;
         }
         prior = __fdiv_rn(__fmul_rn(prior, betahat_prob), beta_prob);
-        f_prior(L, tb)[cs] = prior;
-        f_pred_prob(L, tb)[cs] = pred_prob;
+        rec_store_new_child(L, tb, cs, prior);   // visit 0, no children, hidden index -1, reward(0.), pred_value(0.)
+        f_pred_prob(L, tb)[cs] = pred_prob;       // (cnode.cpp:14-16); the root readouts return these for never-expanded children
         f_beta(L, tb)[cs] = beta_prob;
         f_beta_hat(L, tb)[cs] = betahat_prob;
-        f_visit(L, tb)[cs] = 0;
-        f_nchild(L, tb)[cs] = 0;
-        f_hidx(L, tb)[cs] = -1;
-        f_reward(L, tb)[cs] = 0.0f;      // CNode ctor: reward(0.), pred_value(0.)  (cnode.cpp:14-16);
-        f_pred_value(L, tb)[cs] = 0.0f;  // the root readouts return these for never-expanded children
     }
     if (lane == 0) {
         f_hidx(L, tb)[slot] = (int16_t)hidx;

@@ -106,19 +106,20 @@ __device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb
                                                    int *__restrict__ act_out, int *g_err)
 {
     uint16_t *path = f_path(L, tb);
-    const uint16_t *nchild = f_nchild(L, tb);
-    const uint16_t *cbase = f_cbase(L, tb);
-    const int *visit = f_visit(L, tb);
-    const float *pred_value = f_pred_value(L, tb);
-    const int16_t *hidx = f_hidx(L, tb);
+    const auto nchild = f_nchild(L, tb);
+    const auto cbase = f_cbase(L, tb);
+    const auto visit = f_visit(L, tb);
+    const auto pred_value = f_pred_value(L, tb);
+    const auto hidx = f_hidx(L, tb);
     uint32_t *mt = f_mt(L, tb);
 
     // round trip 0: tree header, root header, prefetched random words
     int mt_pos = h->mt_pos;
     const float mn = h->mm_min, mx = h->mm_max;
     const int mmc = h->mm_cnt;
-    int C = nchild[0], base = cbase[0], vc = visit[0];
-    float pq = pred_value[0];
+    const RecRegs root = rec_load(L, tb, 0);
+    int C = rec_nchild(root), base = rec_cbase(root), vc = rec_visit(root);
+    float pq = rec_pred_value(root);
     constexpr int kPre = 8;
     uint32_t pre = 0;                          // lane l < kPre holds raw state word mt_pos + l (if in this block)
     if (lane < kPre && mt_pos + lane < kMtN) pre = mt[mt_pos + lane];
@@ -131,17 +132,17 @@ __device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb
         // round trip `len+1`: children fields + the children's own headers
         float prior = 0.f, rew = 0.f, ws = 0.f, wt = 1.f, cpq = 0.f;
         int cvis = 0, cC = 0, cbase_c = 0, chidx = -1;
-        if (lane < C) {
-            const int cs = base + lane;
-            prior = f_prior(L, tb)[cs];
-            cvis = visit[cs];
-            rew = f_reward(L, tb)[cs];
-            cC = nchild[cs];
-            cbase_c = cbase[cs];
-            cpq = pred_value[cs];
-            chidx = hidx[cs];
-            ws = f_wsum(L, tb)[cs];   // unconditional (garbage for never-visited children, unused then):
-            wt = f_wtot(L, tb)[cs];   // keeps every load of this level in ONE round trip
+        if (lane < C) {                       // the child's whole record: two 16-byte loads, ONE round trip per level
+            const RecRegs r = rec_load(L, tb, base + lane);
+            prior = rec_prior(r);
+            cvis = rec_visit(r);
+            rew = rec_reward(r);
+            cC = rec_nchild(r);
+            cbase_c = rec_cbase(r);
+            cpq = rec_pred_value(r);
+            chidx = rec_hidx(r);
+            ws = rec_wsum(r);                 // (zero for never-visited children, unused then)
+            wt = rec_wtot(r);
         }
         int ci;
         if (node == 0 && vc <= C) {
@@ -265,7 +266,9 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
     const uint16_t *path = f_path(L, tb);
     const uint32_t *vk = f_vskey(L, tb);
     const float *vv = f_vsval(L, tb);
-    float *reward = f_reward(L, tb), *wsum = f_wsum(L, tb), *wtot = f_wtot(L, tb);
+    const auto reward = f_reward(L, tb);
+    const auto wsum = f_wsum(L, tb);
+    const auto wtot = f_wtot(L, tb);
 
     MAZ_TS(L, tree, lane, 1);
     // ---- round trip 2: issue everything that depends only on the header -------------------------------------
@@ -293,11 +296,12 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
     float my_rew = 0.f, my_ws = 0.f, my_wt = 0.f, my_ppv = 0.f;
     int my_vis = 0, my_hidx = 0;
     if (fast && lane < len) {                         // the leaf (lane == len) is filled by the expansion below
-        my_rew = reward[my_slot];
-        my_ws = wsum[my_slot];
-        my_wt = wtot[my_slot];
-        my_vis = f_visit(L, tb)[my_slot];
-        my_hidx = f_eid(L, tb)[my_slot];
+        const RecRegs r = rec_load(L, tb, my_slot);
+        my_rew = rec_reward(r);
+        my_ws = rec_wsum(r);
+        my_wt = rec_wtot(r);
+        my_vis = rec_visit(r);
+        my_hidx = rec_eid(r);
     }
     {
         const int prev = __shfl_up_sync(MAZ_FULL, my_slot, 1);
@@ -467,7 +471,9 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
         const uint16_t *path = f_path(L, tb);
         const uint32_t *vk = f_vskey(L, tb);
         const float *vv = f_vsval(L, tb);
-        float *reward = f_reward(L, tb), *wsum = f_wsum(L, tb), *wtot = f_wtot(L, tb);
+        const auto reward = f_reward(L, tb);
+    const auto wsum = f_wsum(L, tb);
+    const auto wtot = f_wtot(L, tb);
         const bool fast = len < 32;
         int my_slot = 0;
         if (fast && lane <= len) my_slot = path[lane];
@@ -483,11 +489,12 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
         float my_rew = 0.f, my_ws = 0.f, my_wt = 0.f, my_ppv = 0.f;
         int my_vis = 0, my_eid = 0;
         if (fast && lane < len) {
-            my_rew = reward[my_slot];
-            my_ws = wsum[my_slot];
-            my_wt = wtot[my_slot];
-            my_vis = f_visit(L, tb)[my_slot];
-            my_eid = f_eid(L, tb)[my_slot];
+            const RecRegs r = rec_load(L, tb, my_slot);
+            my_rew = rec_reward(r);
+            my_ws = rec_wsum(r);
+            my_wt = rec_wtot(r);
+            my_vis = rec_visit(r);
+            my_eid = rec_eid(r);
         }
         {
             const int prev = __shfl_up_sync(MAZ_FULL, my_slot, 1);

@@ -1,9 +1,12 @@
 // tree_layout.h -- HBM layout of one batch of search trees (shared by host and device code).
 //
-// One SLAB per tree, slabs back to back in one arena.  Inside a slab every node field is its own
-// array over the tree's P = K*(S+2) node slots (structure of arrays), so that the children of a node --
-// which occupy consecutive slots, as in the reference's pool (cnode.cpp:290-293) -- are read by
-// consecutive lanes of the tree's warp with one coalesced request per field.
+// One SLAB per tree, slabs back to back in one arena.  The fields of a node that selection, backup and expansion touch
+// together (prior, reward, pred_value, weighted sum / total weight, visit count, children count / first child, hidden
+// index, expansion order) form ONE 32-byte record per node slot (`NodeRec`): the children of a node occupy consecutive
+// slots, as in the reference's pool (cnode.cpp:290-293), so a tree level is two 16-byte loads per child lane and three
+// cache lines per ten children (the first layout, one array per field, cost nine scattered 4-byte loads per child and
+// level, and the selection turned out to be bound by the NUMBER of load instructions).  The fields only the root readouts
+// need (pred_prob, beta, beta_hat) and the joint actions stay separate arrays over the P = K*(S+2) slots.
 //
 // The reference's per-node SubTreeValueSet (utils.h:18-40: per-depth multisets big/small) becomes a
 // per-TREE append-only value log: entry = (node slot, relative depth, in-big flag | value).  Only
@@ -38,6 +41,19 @@ struct TreeHdr {              // 64 bytes at the start of every slab
 };
 static_assert(sizeof(TreeHdr) == 64, "TreeHdr must be 64 bytes");
 
+struct alignas(16) NodeRec {   // 32 bytes
+    float prior;              // CNode::prior
+    float reward;             // CNode::reward
+    float pred_value;         // CNode::pred_value
+    float wsum;               // SubTreeValueSet::weighted_sum
+    float wtot;               // SubTreeValueSet::tot_weight
+    int visit;                // CNode::visit_count
+    uint16_t nchild, cbase;   // children count, first child slot
+    int16_t hidx;             // hidden_state_index_x (-1: not expanded)
+    uint16_t eid;             // expansion order = index of the node's q-delta entry
+};
+static_assert(sizeof(NodeRec) == 32, "NodeRec must be 32 bytes");
+
 struct TreeLayout {
     int B, N, A, K, S;
     int P;        // node slots per tree = K*(S+2)   (cnode.cpp:562)
@@ -48,8 +64,8 @@ struct TreeLayout {
     const float *pbc_table; // pb_c[n][visit] = (float)((double)logterm[n] * (sqrt((double)n) / (double)(visit + 1))), host-built
     int pbc_dim;            // table is pbc_dim x pbc_dim (0: compute on the device with fp64)
     // byte offsets inside a slab (all multiples of 128)
-    unsigned off_mt, off_prior, off_pred_prob, off_beta, off_beta_hat, off_reward, off_pred_value, off_wsum, off_wtot,
-        off_qdelta, off_visit, off_nchild, off_cbase, off_hidx, off_eid, off_actions, off_expslot, off_path, off_vskey, off_vsval;
+    unsigned off_mt, off_rec, off_pred_prob, off_beta, off_beta_hat, off_qdelta, off_actions, off_expslot, off_path, off_vskey,
+        off_vsval;
 };
 
 // device error codes stored in TreeHdr::err / the handle's global error word
