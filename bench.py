@@ -99,9 +99,16 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def samples(self):
+        try:
+            self.f.flush()
+            return sum(1 for r in open(self.f.name) if r.strip())
+        except Exception:
+            return 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -319,6 +326,13 @@ def run_ours(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev = timed(lambda i: dev_step(100 + i), args.steps, max(args.warmup, 3))
+    # a default run times 10 x 3.6 ms: shorter than nvidia-smi's start-up.  Keep the GPU under the same load (untimed steps,
+    # the same number on every rank: ms_dev is the all-reduced maximum) until ~0.4 s have passed, so that the clocks are
+    # sampled under load and never missing.
+    extra = int(max(0.0, 0.4 - args.steps * ms_dev * 1e-3) / (ms_dev * 1e-3)) + 1
+    for i in range(extra):
+        dev_step(1000 + i)
+    torch.cuda.synchronize(dev)
     clocks = sampler.stop() if sampler else None
     plan.tree.check()
 
