@@ -62,6 +62,7 @@ class Tree_batch:
         self.simulation_num = int(simulation_num)
         self._h = C.c_void_p()
         self._cache = {}
+        self._cache_dev = {}     # marshalled device pointers of the last readout_device target
         seed = int(random_seed) & 0xFFFFFFFF
         if device is None:
             rc = lib.maz_tree_create(C.byref(self._h), self.root_num, self.agent_num, self.action_space_size,
@@ -197,7 +198,13 @@ class Tree_batch:
         spec = [("value", "float32", B), ("marginal_visit_count", "int32", B * N * A), ("marginal_priors", "float32", B * N * A),
                 ("num_children", "int32", B), ("actions", "int32", B * K * N), ("visit_count", "int32", B * K)]
         spec += [(f, "float32", B * K) for f in _FLOAT_FIELDS]
-        ptrs = [(_dev_ptr(out[k], dt, n, k) if k in out and out[k] is not None else C.c_void_p(0)) for k, dt, n in spec]
+        # the on-device search reads out into the same dict of views every time: validate and marshal the pointers once
+        ck = ("readout_dev", id(out))
+        ptrs = self._cache_dev.get(ck)
+        if ptrs is None or any(p.value != (out[k].data_ptr() if k in out and out[k] is not None else None)
+                               for p, (k, _, _) in zip(ptrs, spec)):
+            ptrs = [(_dev_ptr(out[k], dt, n, k) if k in out and out[k] is not None else C.c_void_p(0)) for k, dt, n in spec]
+            self._cache_dev = {ck: ptrs}
         check(lib.maz_tree_readout_dev(self._h, float(discount), *ptrs))
 
     def _ragged(self, name, discount=0.0):

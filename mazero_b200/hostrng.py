@@ -40,14 +40,43 @@ def _eligible(rs, alpha, A, rows):
     return rs is not None and 0.0 < alpha < 1.0 and rows * A >= 512
 
 
+class _Worker:
+    """ONE persistent background thread for the speculative draws (starting a thread per search costs ~50 us)."""
+
+    def __init__(self):
+        self.cv = threading.Condition()
+        self.job = None
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        while True:
+            with self.cv:
+                while self.job is None:
+                    self.cv.wait()
+                job, self.job = self.job, None
+            job._run()
+
+    def submit(self, job):
+        with self.cv:
+            self.job = job          # (a job that was never picked up is simply superseded: its result would be stale)
+            self.cv.notify()
+
+
+_worker = None
+
+
 class Speculation:
-    __slots__ = ("params", "key0", "pos0", "key1", "pos1", "out", "thread", "error")
+    __slots__ = ("params", "key0", "pos0", "key1", "pos1", "out", "done", "error")
 
     def __init__(self, key0, pos0, params):
+        global _worker
         self.params, self.key0, self.pos0 = params, key0, pos0
         self.key1, self.pos1, self.out, self.error = key0.copy(), pos0, None, None
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        self.done = threading.Event()
+        if _worker is None:
+            _worker = _Worker()
+        _worker.submit(self)
 
     def _run(self):
         try:
@@ -55,6 +84,11 @@ class Speculation:
             self.out, self.pos1 = _draw(self.key1, self.pos0, alpha, A, rows)
         except Exception as e:     # the caller falls back to the ordinary draw
             self.error = e
+        self.done.set()
+
+    def wait(self, timeout=0.05):
+        """True when the result is there; a job that was superseded before it started never finishes."""
+        return self.done.wait(timeout)
 
 
 _pending = {}   # id(RandomState) -> Speculation
@@ -81,9 +115,8 @@ def dirichlet_f32(np_random, alpha, A, rows):
         if st[0] == "MT19937":
             sp = _pending.pop(id(rs), None)
             if sp is not None:
-                sp.thread.join()
-                if sp.error is None and sp.params == (alpha, int(A), int(rows)) and sp.pos0 == int(st[2]) and \
-                        np.array_equal(sp.key0, st[1]):
+                if sp.params == (alpha, int(A), int(rows)) and sp.pos0 == int(st[2]) and np.array_equal(sp.key0, st[1]) \
+                        and sp.wait() and sp.error is None:
                     rs.set_state(("MT19937", sp.key1, sp.pos1, st[3], st[4]))
                     STATS["used"] += 1
                     return sp.out
