@@ -384,6 +384,20 @@ class _DevicePlan:
         self.graphs[self.cur] = g
 
 
+# The workers build a NEW `SampledMCTS(config, np_random)` for every environment step / every agent
+# (selfplay_worker.py:191, reanalyze_worker.py:284), so the expensive device objects -- packed weights, tree arena,
+# hidden-state pool, captured CUDA graphs -- are cached per PROCESS, not per instance: keyed by the model object and
+# the problem shape / search constants.  An instance's `_inference` / `_plans` list what that instance used.
+_INFERENCE_CACHE = {}   # (id(model), device) -> (weakref to the model, SmacInference | MlpInference)
+_PLAN_CACHE = {}        # (id(inference), B, K, S, joint, tau, search constants, use_graph) -> _DevicePlan
+
+
+def clear_caches():
+    """Drop every cached device object (arenas, pools, graphs) of this process."""
+    _INFERENCE_CACHE.clear()
+    _PLAN_CACHE.clear()
+
+
 class SampledMCTS(object):
     def __init__(self, config, np_random: np.random.RandomState = None, use_cuda_graph: bool = True,
                  inference_mode: str = "auto", speculate_noise: bool = True):
@@ -417,12 +431,12 @@ class SampledMCTS(object):
         if dev.type != "cuda":
             return None
         key = (id(model), str(dev))
-        inf = self._inference.get(key)
+        hit = _INFERENCE_CACHE.get(key)
+        inf = hit[1] if hit is not None and hit[0]() is model else None      # (ids are reused after garbage collection)
         version = sum(int(getattr(p, "_version", 0)) for p in sd.values())
         if inf is None and mlp:
             inf = MlpInference.from_model(model, device=dev, mode="torch" if self.inference_mode == "torch" else "fp32")
             inf._src_version = version
-            self._inference[key] = inf
         elif inf is None:
             mode = self.inference_mode
             if mode == "auto":
@@ -432,10 +446,12 @@ class SampledMCTS(object):
                 mode = "bf16" if fused.supported(sd, int(model.num_agents), int(model.action_space_size), h) else "fp32"
             inf = SmacInference.from_model(model, device=dev, mode=mode)
             inf._src_version = version
-            self._inference[key] = inf
         elif getattr(inf, "_src_version", None) != version:   # weights were updated in place (set_weights)
             inf.refresh(sd)
             inf._src_version = version
+        import weakref
+        _INFERENCE_CACHE[key] = (weakref.ref(model), inf)
+        self._inference[key] = inf
         return inf
 
     # ---- the entry point (mcts_sampled.py:34-46) -----------------------------------------------------------
@@ -522,12 +538,16 @@ class SampledMCTS(object):
 
     def _plan(self, inf, B, current_agent_idx, sampled_tau) -> _DevicePlan:
         cfg = self.config
-        key = (id(inf), B, cfg.sampled_action_times, cfg.num_simulations, current_agent_idx is None, float(sampled_tau))
-        plan = self._plans.get(key)                                                  # all sequential turns share a plan
+        key = (id(inf), B, cfg.sampled_action_times, cfg.num_simulations, current_agent_idx is None, float(sampled_tau),
+               float(cfg.pb_c_base), float(cfg.pb_c_init), float(cfg.discount), bool(self.use_cuda_graph))
+        plan = _PLAN_CACHE.get(key)                                                  # all sequential turns share a plan
+        if plan is not None and plan.inf is not inf:
+            plan = None
         if plan is None:
             plan = _DevicePlan(inf, B, cfg.sampled_action_times, cfg.num_simulations, current_agent_idx, cfg, sampled_tau,
                                self.use_cuda_graph)
-            self._plans[key] = plan
+            _PLAN_CACHE[key] = plan
+        self._plans[key] = plan
         return plan
 
     # ---- the workers' per-agent loop as ONE device-resident call ------------------------------------------

@@ -211,3 +211,35 @@ def test_sequential_turns_share_one_plan_without_leaking_state(built_lib):
         assert np.array_equal(o.value, fresh.value)
         assert np.array_equal(o.marginal_visit_count, fresh.marginal_visit_count)
         assert o.sampled_qvalues == fresh.sampled_qvalues
+
+
+def test_new_instances_reuse_the_cached_device_objects(built_lib):
+    """The workers build a new SampledMCTS per environment step / per agent (selfplay_worker.py:191, reanalyze_worker.py:284):
+    packed weights, tree arena, hidden-state pool and captured graphs are cached per process, keyed by the model object and
+    the problem shape, and a search through a new instance gives the same bits as through the first one."""
+    from mazero_b200 import mcts_sampled
+    from mazero_b200.mcts_sampled import SampledMCTS
+
+    N, A, B, K, S = 3, 9, 16, 5, 10
+    cfg = MockConfig(N, A, S, K)
+    model = smac_model(N, A).cuda()
+    model.hidden_state_size_per_agent = model.hidden
+    out0 = root_output(smac_model(N, A), B)
+    out0 = out0._replace(hidden_state=out0.hidden_state.cuda())
+    first = SampledMCTS(cfg, np.random.RandomState(3))
+    r1 = first.batch_search(model, out0, 1, None, N, None, torch.device("cuda:0"), add_noise=True)
+    second = SampledMCTS(cfg, np.random.RandomState(3))
+    r2 = second.batch_search(model, out0, 1, None, N, None, torch.device("cuda:0"), add_noise=True)
+    assert next(iter(first._plans.values())) is next(iter(second._plans.values()))
+    assert next(iter(first._inference.values())) is next(iter(second._inference.values()))
+    assert np.array_equal(r1.value, r2.value) and np.array_equal(r1.marginal_visit_count, r2.marginal_visit_count)
+    assert r1.sampled_qvalues == r2.sampled_qvalues
+    # another configuration of the search constants does not share the plan
+    cfg2 = MockConfig(N, A, S, K)
+    cfg2.discount = 0.9
+    third = SampledMCTS(cfg2, np.random.RandomState(3))
+    third.batch_search(model, out0, 1, None, N, None, torch.device("cuda:0"), add_noise=True)
+    assert next(iter(third._plans.values())) is not next(iter(first._plans.values()))
+    n = len(mcts_sampled._PLAN_CACHE)
+    mcts_sampled.clear_caches()
+    assert n >= 2 and not mcts_sampled._PLAN_CACHE
