@@ -20,13 +20,6 @@ __device__ __forceinline__ float warp_sum(float v)
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ float warp_max(float v)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // k_root_prepare: one warp per (root, agent) row of the logits.  Rows of tree agents produce probs / beta / noise;
 // every row produces its greedy action.

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 import ctypes as C
+import weakref
 
 from . import cytree, hostrng
 from ._lib import check, lib
@@ -129,7 +130,6 @@ class _DevicePlan:
         # ---- host -> device staging: every small root input lives in ONE pinned buffer (one H2D copy per search) ----
         T = 1 if cur is None else self.N            # turns served by this plan (sequential-agent mode: one per agent)
         self.T = T
-        NA = self.N * self.A
         in_spec = [("rewards", f32, (B,)), ("values", f32, (B,)), ("logits", f32, (B, self.N, self.A)),
                    ("legal", f32, (B, self.N, self.A)), ("factor_in", i32, (B, self.N))]
         for t in range(T):    # per-turn block (depends on the host RNG): contiguous, so one H2D copy per turn
@@ -449,7 +449,6 @@ class SampledMCTS(object):
         elif getattr(inf, "_src_version", None) != version:   # weights were updated in place (set_weights)
             inf.refresh(sd)
             inf._src_version = version
-        import weakref
         _INFERENCE_CACHE[key] = (weakref.ref(model), inf)
         self._inference[key] = inf
         return inf
