@@ -94,3 +94,30 @@ def test_speculative_draw_is_used_only_when_the_generator_is_untouched(built_lib
     sa, sb = a.get_state(), b.get_state()
     assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
     assert hostrng.STATS["used"] - used0 == 2 and hostrng.STATS["discarded"] - disc0 == 3   # used after steps 0, 2; discarded after steps 1, 3 and for the other shape
+
+
+def test_parallel_dirichlet_property(built_lib):
+    """Random shapes / concentrations / stream positions (hypothesis): always bit-identical to numpy, values and state."""
+    from hypothesis import given, settings, strategies as st
+
+    from mazero_b200 import hostrng
+
+    @settings(max_examples=40, deadline=None)
+    @given(seed=st.integers(0, 2**31 - 1), rows=st.integers(64, 3000), A=st.integers(2, 40),
+           alpha=st.floats(0.02, 0.98), burn=st.integers(0, 1300), threads=st.sampled_from([0, 1, 3]))
+    def check(seed, rows, A, alpha, burn, threads):
+        a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+        a.random_sample(burn); b.random_sample(burn)
+        if rows * A < 512:
+            rows = 512 // A + 1
+        hostrng.THREADS = threads
+        try:
+            ref = a.dirichlet([alpha] * A, rows).astype(np.float32)
+            got = hostrng.dirichlet_f32(b, alpha, A, rows)
+        finally:
+            hostrng.THREADS = 0
+        assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+        sa, sb = a.get_state(), b.get_state()
+        assert sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+
+    check()
