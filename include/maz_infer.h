@@ -45,6 +45,12 @@ typedef struct maz_infer_desc {
     int o_bin, o_pos, o_layer, o_dyn, o_rg, o_vg, o_pol;   /* float offsets into vec */
     long long *dbg_clock;        /* optional (NULL): SM-cycle timestamps of CTA 0's stages, 256 entries (profiling) */
     int dbg_flags;               /* profiling only: 1 = skip the epilogue math, 2 = skip the MMAs (results are garbage) */
+    int roots_per_tile;          /* small-batch kernel only: whole roots per 32-row tile, 0 = floor(32 / N) */
+    /* Sequential-agent mode with the joint action assembled IN the kernel (mcts_sampled.py:116-147), when greedy_pool is
+     * non-NULL and cur >= 0: `actions` is then the TREE's action (B,1) of agent `cur`; agents k < cur take factor[b][k]
+     * (zeros when factor is NULL), agents k > cur take greedy_pool[idx_x[b]][b][k] = argmax_a prediction(parent).policy. */
+    const int *factor;           /* (B,N) or NULL */
+    const int *greedy_pool;      /* (S+1,B,N): row (idx*B + b), or NULL (`actions` is the full (B,N) joint action) */
 } maz_infer_desc;
 
 /* replaces model.recurrent_inference + the driver's softmax/beta (mcts_sampled.py:150-161): one kernel launch */
@@ -58,6 +64,9 @@ int maz_infer_recurrent_small(const maz_infer_desc *desc, void *cuda_stream);
 /* number of column groups the small-batch kernel was compiled for (4 or 8): the stacked graph-net weights are
  * interleaved in groups of 64 / nq features (gc rows, then nn rows) by the host-side packer. */
 int maz_infer_small_nq(void);
+/* opt both kernels into their dynamic shared-memory sizes ahead of time (called by maz_search_create, so that the launches
+ * captured into a CUDA graph do not have to); vec_floats / ka as in the descriptor */
+int maz_infer_configure(int vec_floats, int ka);
 
 /* ---- MLP-family network (the reference's matrix-game MAMuZeroNet) --------------------------------------------
  * Replaces, for the search only, config/matrix/model.py:358-368 `recurrent_inference` (= `dynamics` :334-343 /
@@ -93,6 +102,8 @@ typedef struct maz_mlp_desc {
                                          fc_value (N*H -> support), fc_policy (H -> A, applied per agent) */
     int reward_support_min, reward_support_size;   /* size 1: scalar head, no transform (use_vectorization=False) */
     int value_support_min, value_support_size;
+    const int *factor;           /* in-kernel joint-action assembly of the sequential-agent mode: see maz_infer_desc */
+    const int *greedy_pool;
 } maz_mlp_desc;
 
 int maz_mlp_recurrent(const maz_mlp_desc *desc, void *cuda_stream);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "maz_infer_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maz_infer_recurrent_small": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maz_infer_small_nq": (C.c_int, []),
+    "maz_infer_configure": (C.c_int, [C.c_int, C.c_int]),
     "maz_mlp_recurrent": (C.c_int, [C.c_void_p, C.c_void_p]),
     "maz_mlp_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     # include/maz_hostrng.h
@@ -60,6 +61,23 @@ SIGNATURES = {
     "maz_agent_turn_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    # include/maz_search.h
+    "maz_search_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p]),
+    "maz_search_destroy": (None, [C.c_void_p]),
+    "maz_search_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "maz_search_strategy": (C.c_int, [C.c_void_p]),
+    "maz_search_device_bytes": (C.c_size_t, [C.c_void_p]),
+    "maz_search_pool": (C.c_void_p, [C.c_void_p]),
+    "maz_search_tree": (C.c_void_p, [C.c_void_p]),
+    "maz_search_root_arrays": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "maz_search_run_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "maz_search_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "maz_search_check": (C.c_int, [C.c_void_p]),
+    "maz_search_set_record": (C.c_int, [C.c_void_p] * 7),
+    "maz_search_set_debug_clock": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "maz_search_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "maz_search_loop_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "maz_search_roots_per_cta": (C.c_int, [C.c_void_p]),
 }
 
 if not os.path.exists(LIB_PATH):

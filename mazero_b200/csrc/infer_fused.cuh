@@ -769,7 +769,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference(const __gri
         if (valid) {
             const int ix = d.idx_x ? __ldcg(d.idx_x + root) : 0;   // .cg: produced by the kernel we may have overlapped (PDL)
             hrow = d.pool + ((size_t)ix * d.B + root) * (size_t)(N * H) + (size_t)agent * H;
-            my_action = __ldcg(d.actions + (size_t)root * N + agent);
+            if (d.greedy_pool == nullptr || d.cur < 0)
+                my_action = __ldcg(d.actions + (size_t)root * N + agent);
+            else if (agent == d.cur)                  // sequential-agent mode, joint action assembled here (mcts_sampled.py:116-147)
+                my_action = __ldcg(d.actions + root);
+            else if (agent < d.cur)
+                my_action = d.factor ? __ldcg(d.factor + (size_t)root * N + agent) : 0;
+            else
+                my_action = __ldcg(d.greedy_pool + ((size_t)ix * d.B + root) * N + agent);
         }
         gather_hidden(hrow, valid, aT);
         if (t.part * 16 < KA) {

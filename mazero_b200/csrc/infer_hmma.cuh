@@ -52,6 +52,12 @@ constexpr uint32_t SLOT_BYTES = 128 * (H + PAD) * 2;
 #define MAZ_HMMA_PIECE 4352
 #endif
 constexpr uint32_t PIECE = MAZ_HMMA_PIECE;   // bytes per bulk-copy request (16 weight rows)
+// k-loop unrolling of the GEMM stages: 2 keeps the double-buffered fragment indices compile-time and the code small (the kernel
+// runs ~25 different stages once per simulation: its instruction footprint, not its loop overhead, is what costs)
+#ifndef MAZ_GEMM_UNROLL
+#define MAZ_GEMM_UNROLL 2
+#endif
+constexpr int GEMM_UNROLL = MAZ_GEMM_UNROLL;
 
 // ---- shared-memory map (compile-time offsets from the dynamic base: every access is a plain LDS / STS) -------------
 constexpr uint32_t OFF_X = 0;                                    // activation tile X        [TM][LDA]
@@ -77,6 +83,24 @@ static_assert(TM * 2 * 12 * 4 <= 3 * TM * NQ * 8, "head logits must fit in the s
 using Desc = ::maz_infer_desc;
 
 struct RowInfo { int root, agent, valid, r0; };   // r0 = first row of my root inside the tile
+
+// whole roots per 32-row tile (the persistent search kernel owns fewer roots per CTA than fit: one warp per tree)
+__device__ __forceinline__ int tile_rpt(const Desc &d) { return d.roots_per_tile > 0 ? d.roots_per_tile : TM / d.N; }
+
+// The per-simulation pointers: constants of the descriptor for the one-step kernel, advanced per simulation by the
+// persistent whole-search kernel (search_persist.cuh).
+struct SimIo {
+    const int *idx_x;      // (B,) pool index of the parent
+    const int *actions;    // (B,N) joint action, or (B,1) tree action when the joint action is assembled here
+    float *next_hidden;    // (B, N*H)
+    float *reward, *value, *probs, *beta;
+    int *greedy;           // (B,N) or NULL
+    float *logits_out;     // (B,N,A) or NULL
+};
+__device__ __forceinline__ SimIo io_from_desc(const Desc &d)
+{
+    return SimIo{d.idx_x, d.actions, d.next_hidden, d.reward, d.value, d.probs, d.beta, d.greedy, d.logits_out};
+}
 
 __host__ __device__ inline size_t smem_bytes(int vec_floats) { return (size_t)OFF_P + (size_t)vec_floats * 4 + 128; }
 
@@ -149,7 +173,7 @@ __device__ __forceinline__ void gemm_fixed(float (&acc)[NT][4], const Thr &th, u
     ldsm4(aa, a[0]);
 #pragma unroll
     for (int p = 0; p < NT / 2; ++p) ldsm4(wa + (uint32_t)(16 * p) * ldw, b[0][p]);
-#pragma unroll
+#pragma unroll GEMM_UNROLL
     for (int ks = 0; ks < KS; ++ks) {
         const int cur = ks & 1, nxt = cur ^ 1;
         if (ks + 1 < KS) {
@@ -311,7 +335,7 @@ __device__ __forceinline__ RowInfo row_info(int r)
 
 // ---- stages (not inlined: the kernel is one long straight line, small code keeps the instruction cache warm) ----------
 // fp32 pool rows -> bf16 tile HH; one-hot joint action -> tile One.  Thread (row = tid/8, 16 columns each).
-__device__ __noinline__ void stage_gather(const Desc &d)
+static __device__ __noinline__ void stage_gather(const Desc &d, const SimIo io)
 {
     HSM_DECL;
     const int tid = threadIdx.x, r = tid >> 3, part = tid & 7;
@@ -320,8 +344,15 @@ __device__ __noinline__ void stage_gather(const Desc &d)
     uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int action = -1;
     if (ri.valid) {
-        const int ix = d.idx_x ? __ldcg(d.idx_x + ri.root) : 0;
-        action = __ldcg(d.actions + (size_t)ri.root * d.N + ri.agent);
+        const int ix = io.idx_x ? __ldcg(io.idx_x + ri.root) : 0;
+        if (d.greedy_pool == nullptr || d.cur < 0)
+            action = __ldcg(io.actions + (size_t)ri.root * d.N + ri.agent);
+        else if (ri.agent == d.cur)                   // sequential-agent mode (mcts_sampled.py:116-147): the tree's action,
+            action = __ldcg(io.actions + ri.root);
+        else if (ri.agent < d.cur)                    // ... the earlier agents' chosen actions,
+            action = d.factor ? __ldcg(d.factor + (size_t)ri.root * d.N + ri.agent) : 0;
+        else                                          // ... argmax_a prediction(parent).policy for the later agents
+            action = __ldcg(d.greedy_pool + ((size_t)ix * d.B + ri.root) * d.N + ri.agent);
         const float *h = d.pool + ((size_t)ix * d.B + ri.root) * (size_t)(d.N * H) + (size_t)ri.agent * H + part * 16;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -343,7 +374,7 @@ __device__ __noinline__ void stage_gather(const Desc &d)
 }
 
 // x0 = relu(W_in [h | onehot] + b) + pos[agent]  -> residual fragment x, bf16 tile X
-__device__ __noinline__ void stage_inproj(const Desc &d, Ring &ring, float (&xio)[NT][4])
+static __device__ __noinline__ void stage_inproj(const Desc &d, Ring &ring, float (&xio)[NT][4])
 {
     const Thr th;
     const uint32_t sb = sbase();
@@ -372,7 +403,7 @@ __device__ __noinline__ void stage_inproj(const Desc &d, Ring &ring, float (&xio
 
 // q | k | v = X W^T + b  -> bf16 rows in Q (stride LDQ).  ONE pass over the activations: the three weight chunks are
 // resident together (all ring slots), the A fragment of a k-step feeds 3*NT MMAs.
-__device__ __noinline__ void stage_qkv(Ring &ring, uint32_t lv)
+static __device__ __noinline__ void stage_qkv(Ring &ring, uint32_t lv)
 {
     const Thr th;
     const uint32_t sb = sbase();
@@ -388,7 +419,7 @@ __device__ __noinline__ void stage_qkv(Ring &ring, uint32_t lv)
     ldsm4(aa, a[0]);
 #pragma unroll
     for (int p = 0; p < NP; ++p) ldsm4(wa[p / PW] + (uint32_t)(16 * (p % PW)) * LDA, b[0][p]);
-#pragma unroll
+#pragma unroll GEMM_UNROLL
     for (int ks = 0; ks < 8; ++ks) {
         const int cur = ks & 1, nxt = cur ^ 1;
         if (ks + 1 < 8) {
@@ -472,7 +503,7 @@ __device__ __forceinline__ void attention_small(uint32_t qbase, int r0, int hh, 
     }
 }
 
-__device__ __noinline__ void stage_attention(const Desc &d)
+static __device__ __noinline__ void stage_attention(const Desc &d)
 {
     const uint32_t sb = sbase(), qbase = sb + OFF_Q;
     const int tid = threadIdx.x, r = tid >> 3, hh = tid & 7;
@@ -533,7 +564,7 @@ __device__ __noinline__ void stage_attention(const Desc &d)
 }
 
 // x = LN(x + T W^T + b) * g + be   (post-LN residual block: out-proj / linear2) -> fragment x, bf16 tile X
-__device__ __noinline__ void stage_residual_ln(Ring &ring, float (&xio)[NT][4], uint32_t bias, uint32_t gam, uint32_t bet)
+static __device__ __noinline__ void stage_residual_ln(Ring &ring, float (&xio)[NT][4], uint32_t bias, uint32_t gam, uint32_t bet)
 {
     const Thr th;
     const uint32_t sb = sbase();
@@ -551,7 +582,7 @@ __device__ __noinline__ void stage_residual_ln(Ring &ring, float (&xio)[NT][4], 
 }
 
 // f = relu(X W1^T + b1) -> bf16 tile T
-__device__ __noinline__ void stage_linear_relu(Ring &ring, uint32_t bias)
+static __device__ __noinline__ void stage_linear_relu(Ring &ring, uint32_t bias)
 {
     const Thr th;
     const uint32_t sb = sbase();
@@ -569,7 +600,7 @@ __device__ __noinline__ void stage_linear_relu(Ring &ring, uint32_t bias)
 
 // fc_dynamic (model.py:262-268): [h | onehot | attn] -> Linear LN ReLU -> Linear LN ReLU -> Linear, + h; next_hidden to
 // global (fp32) and to tile T (bf16)
-__device__ __noinline__ void stage_dynamics(const Desc &d, Ring &ring)
+static __device__ __noinline__ void stage_dynamics(const Desc &d, Ring &ring, const SimIo io)
 {
     const Thr th;
     const uint32_t sb = sbase();
@@ -604,7 +635,7 @@ __device__ __noinline__ void stage_dynamics(const Desc &d, Ring &ring)
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
         const RowInfo &ri = hf ? rb : ra;
-        const int ix = (ri.valid && d.idx_x) ? __ldcg(d.idx_x + ri.root) : 0;
+        const int ix = (ri.valid && io.idx_x) ? __ldcg(io.idx_x + ri.root) : 0;
         const float *hp = d.pool + ((size_t)ix * d.B + (ri.valid ? ri.root : 0)) * (size_t)(d.N * H) + (size_t)ri.agent * H;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
@@ -618,7 +649,7 @@ __device__ __noinline__ void stage_dynamics(const Desc &d, Ring &ring)
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
         const RowInfo &ri = hf ? rb : ra;
-        float *nh = d.next_hidden + (size_t)(ri.valid ? ri.root : 0) * (d.N * H) + (size_t)ri.agent * H;
+        float *nh = io.next_hidden + (size_t)(ri.valid ? ri.root : 0) * (d.N * H) + (size_t)ri.agent * H;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             acc[nt][2 * hf] += hv[hf][nt].x;
@@ -671,17 +702,12 @@ __device__ __forceinline__ void gnn_phase_b(const float (&acc)[NT][4], const Thr
     float2 sa[GT], sc[GT];
 #pragma unroll
     for (int tl = 0; tl < GT; ++tl) sa[tl] = sc[tl] = make_float2(0.f, 0.f);
-    switch (N) {                       // CTA-uniform
-        case 1: agent_sums<1>(G, f0, r0A, r0B, sa, sc); break;
-        case 2: agent_sums<2>(G, f0, r0A, r0B, sa, sc); break;
-        case 3: agent_sums<3>(G, f0, r0A, r0B, sa, sc); break;
-        default: {
-            int j = 0;
+    {
+        int j = 0;
 #pragma unroll 1
-            for (; j + 4 <= N; j += 4) agent_sums<4>(G, f0, r0A + j, r0B + j, sa, sc);
+        for (; j + 3 <= N; j += 3) agent_sums<3>(G, f0, r0A + j, r0B + j, sa, sc);
 #pragma unroll 1
-            for (; j < N; ++j) agent_sums<1>(G, f0, r0A + j, r0B + j, sa, sc);
-        }
+        for (; j < N; ++j) agent_sums<1>(G, f0, r0A + j, r0B + j, sa, sc);
     }
 #pragma unroll
     for (int tl = 0; tl < GT; ++tl) {
@@ -705,7 +731,7 @@ __device__ __forceinline__ void gnn_phase_c(const Thr &th, uint32_t stat, float 
 
 // heads, first layers, ONE stage: reward GNN layer 1 on [next_hidden | onehot], value GNN layer 1 and fc_policy.0 on
 // next_hidden.  Outputs: X[:, 0:64] = reward features, X[:, 64:128] = value features, Ph = relu(LN(policy hidden)).
-__device__ __noinline__ void stage_heads1(const Desc &d, Ring &ring)
+static __device__ __noinline__ void stage_heads1(const Desc &d, Ring &ring)
 {
     const Thr th;
     const uint32_t sb = sbase();
@@ -788,7 +814,7 @@ __device__ __forceinline__ float support_to_scalar(uint32_t lg)
 
 // heads, second layers + outputs, ONE stage: reward / value GNN layer 2 -> mean over agents -> 64->11 head -> scalar;
 // fc_policy.3 -> softmax / beta / greedy (mcts_sampled.py:158-161).
-__device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
+static __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring, const SimIo io)
 {
     const Thr th;
     const uint32_t sb = sbase();
@@ -866,17 +892,17 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
         }
         HS();
         if (ri.valid) {
-            if (d.greedy && sub == 0) d.greedy[(size_t)ri.root * N + ri.agent] = am;
+            if (io.greedy && sub == 0) io.greedy[(size_t)ri.root * N + ri.agent] = am;
             const int ta = (d.cur < 0) ? ri.agent : (ri.agent == d.cur ? 0 : -1);
             const float invs = 1.f / s, invb = 1.f / sbeta;
             for (int a = sub; a < A; a += 8) {
                 const float v = lds1v(lg + 4u * a);
-                if (d.logits_out) d.logits_out[((size_t)ri.root * N + ri.agent) * A + a] = v;
+                if (io.logits_out) io.logits_out[((size_t)ri.root * N + ri.agent) * A + a] = v;
                 if (ta >= 0) {
                     const float e = __expf(v - m);
                     const size_t o = ((size_t)ri.root * d.Nt + ta) * A + a;
-                    d.probs[o] = e * invs;
-                    d.beta[o] = (unit_tau ? e : __powf(e, d.inv_tau)) * invb;
+                    io.probs[o] = e * invs;
+                    io.beta[o] = (unit_tau ? e : __powf(e, d.inv_tau)) * invb;
                 }
             }
         }
@@ -898,7 +924,7 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
     cta_sync();
     HS();
     // phase D: mean over the agents of a root -> pooled[kind][root][f] (fp32) in the X + T tiles (free since the GEMMs above)
-    const int rpt = TM / N;
+    const int rpt = tile_rpt(d);
     const uint32_t POOL = sb + OFF_X;
     const float invn = 1.f / (float)N;
     for (int i = tid; i < 2 * rpt * (GH / 2); i += NCONS) {
@@ -947,26 +973,19 @@ __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring)
     if (tid < rpt * 2) {
         const int rl = tid >> 1, kind = tid & 1;
         const int root = blockIdx.x * rpt + rl;
-        if (root < d.B) (kind ? d.value : d.reward)[root] = support_to_scalar(LG + 4u * ((rl * 2 + kind) * 12));
+        if (root < d.B) (kind ? io.value : io.reward)[root] = support_to_scalar(LG + 4u * ((rl * 2 + kind) * 12));
     }
     HS();
 #undef HS
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_small(const __grid_constant__ Desc d)
+// ---- pieces shared by the one-step kernel below and the persistent whole-search kernel (search_persist.cuh) -----------
+__device__ __forceinline__ void setup_rows(const Desc &d)     // threads < TM: the tile's row table
 {
     HSM_DECL;
-    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_vec;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int N = d.N;
-
-    if (tid == 0) {
-        for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], NCONS / 32); }
-        mbar_init(&bar_vec, 1);
-        mbar_fence_init();
-    }
+    const int tid = threadIdx.x, N = d.N;
     if (tid < TM) {
-        const int rpt = TM / N, rl = tid / N, agent = tid - rl * N;
+        const int rpt = tile_rpt(d), rl = tid / N, agent = tid - rl * N;
         const int root = blockIdx.x * rpt + rl;
         RowInfo ri;
         ri.valid = (rl < rpt) && (root < d.B);
@@ -974,53 +993,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_small(const
         ri.r0 = (rl < rpt) ? rl * N : 0;
         reinterpret_cast<RowInfo *>(hsm + OFF_ROW)[tid] = ri;
     }
-    __syncthreads();
+}
 
-    if (warp == NCONS / 32) {
-        // ================================ weight producer (one thread) =========================================
-        if ((tid & 31) == 0) {
-            mbar_expect_tx(&bar_vec, (uint32_t)d.vec_floats * 4u);
-            bulk_g2s(hsm + OFF_P, d.vec, (uint32_t)d.vec_floats * 4u, &bar_vec);
+// weight producer (one thread): the fp32 parameter block once, then `rounds` passes over the NCHUNK weight chunks through
+// the NSLOT-deep ring (one pass per recurrent_inference; the persistent kernel keeps streaming across simulations, so the
+// first chunks of simulation s+1 arrive while the CTA runs the tree step of simulation s)
+__device__ __forceinline__ void produce_weights(const Desc &d, uint64_t *bar_full, uint64_t *bar_empty, uint64_t *bar_vec, int rounds)
+{
+    HSM_DECL;
+    mbar_expect_tx(bar_vec, (uint32_t)d.vec_floats * 4u);
+    bulk_g2s(hsm + OFF_P, d.vec, (uint32_t)d.vec_floats * 4u, bar_vec);
+    const int total = rounds * NCHUNK;
 #pragma unroll 1
-            for (int c = 0; c < NCHUNK; ++c) {
-                const int s = c % NSLOT;
-                if (c >= NSLOT) mbar_wait_backoff(&bar_empty[s], ((c / NSLOT) - 1) & 1);
-                // one chunk = several bulk copies on the same mbarrier (16 weight rows each)
-                const uint32_t nbytes = (d.dbg_flags & 4) ? 16u : d.chunk_bytes[c];   // profiling: tiny copies
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(d.wpk) + d.chunk_off[c];
-                uint8_t *dst = hsm + OFF_W + (size_t)s * SLOT_BYTES;
-                mbar_expect_tx(&bar_full[s], nbytes);
-                for (uint32_t o = 0; o < nbytes; o += PIECE) {
-                    const uint32_t n = (nbytes - o < PIECE) ? (nbytes - o) : PIECE;
-                    bulk_g2s(dst + o, src + o, n, &bar_full[s]);
-                }
-            }
+    for (int c = 0, k = 0; c < total; ++c, k = (k + 1 == NCHUNK) ? 0 : k + 1) {
+        const int s = c % NSLOT;
+        if (c >= NSLOT) mbar_wait_backoff(&bar_empty[s], ((c / NSLOT) - 1) & 1);
+        // one chunk = several bulk copies on the same mbarrier (16 weight rows each)
+        const uint32_t nbytes = (d.dbg_flags & 4) ? 16u : d.chunk_bytes[k];   // profiling: tiny copies
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(d.wpk) + d.chunk_off[k];
+        uint8_t *dst = hsm + OFF_W + (size_t)s * SLOT_BYTES;
+        mbar_expect_tx(&bar_full[s], nbytes);
+        for (uint32_t o = 0; o < nbytes; o += PIECE) {
+            const uint32_t n = (nbytes - o < PIECE) ? (nbytes - o) : PIECE;
+            bulk_g2s(dst + o, src + o, n, &bar_full[s]);
         }
-        return;
     }
-    // ==================================== compute warps =========================================================
-    Ring ring{bar_full, bar_empty, 0};
-    int ts_n = 0;
-    const bool ts_on = d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0;
+}
+
+// padded copies of the two 11 x 64 head matrices (conflict-free float4 rows for the final logits); parameters resident
+__device__ __forceinline__ void setup_head_copies(const Desc &d)
+{
+    const uint32_t sb = sbase();
+    for (int i = threadIdx.x; i < 2 * SUP * GH; i += NCONS) {
+        const int f = i % GH, rest = i / GH, k = rest % SUP, kind = rest / SUP;
+        sts1f(sb + OFF_VP + 4u * ((kind * SUP + k) * LDV + f), lds1v(sb + OFF_P + 4u * ((kind ? d.o_vg : d.o_rg) + 256 + k * GH + f)));
+    }
+}
+
+// one recurrent_inference of the CTA's tile: every stage after the gather (compute warps; row table, parameters and head
+// copies are set up).  `clk` (or NULL): SM-cycle timestamps of the stages, written by thread 0.
+__device__ __forceinline__ void infer_stages(const Desc &d, const SimIo io, Ring &ring, long long *clk)
+{
+    int ts_n = 2;
 #define TS() \
-    if (ts_on && ts_n < 64) d.dbg_clock[ts_n++] = clock64();
-    TS();
-    // PDL: everything above (and the producer warp's parameter / weight streaming, which reads constants only) may overlap the
-    // tail of the tree kernel that produces idx_x / actions; wait for it before touching its outputs or the pool.  Only then
-    // may the next tree kernel start: its pre-wait section reads tree state that the kernel we waited for was still writing.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    stage_gather(d);
-    TS();
-    mbar_wait(&bar_vec, 0);          // parameters resident
-    {   // padded copies of the two 11 x 64 head matrices (conflict-free float4 rows for the final logits)
-        const uint32_t sb = sbase();
-        for (int i = tid; i < 2 * SUP * GH; i += NCONS) {
-            const int f = i % GH, rest = i / GH, k = rest % SUP, kind = rest / SUP;
-            sts1f(sb + OFF_VP + 4u * ((kind * SUP + k) * LDV + f), lds1v(sb + OFF_P + 4u * ((kind ? d.o_vg : d.o_rg) + 256 + k * GH + f)));
-        }
-    }
-    cta_sync();
+    if (clk && ts_n < 64) clk[ts_n++] = clock64();
     TS();
     float x[NT][4];
     stage_inproj(d, ring, x);
@@ -1041,14 +1057,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_small(const
         TS();
     }
     TS();
-    stage_dynamics(d, ring);
+    stage_dynamics(d, ring, io);
     TS();
     stage_heads1(d, ring);
     TS();
-    stage_heads2(d, ring);
+    stage_heads2(d, ring, io);
     TS();
 #undef TS
 }
+
+#ifndef MAZ_HMMA_NO_KERNEL
+__global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_small(const __grid_constant__ Desc d)
+{
+    HSM_DECL;
+    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_vec;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], NCONS / 32); }
+        mbar_init(&bar_vec, 1);
+        mbar_fence_init();
+    }
+    setup_rows(d);
+    __syncthreads();
+
+    if (warp == NCONS / 32) {
+        if ((tid & 31) == 0) produce_weights(d, bar_full, bar_empty, &bar_vec, 1);
+        return;
+    }
+    // ==================================== compute warps =========================================================
+    Ring ring{bar_full, bar_empty, 0};
+    long long *clk = (d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0) ? d.dbg_clock : nullptr;
+    if (clk) clk[0] = clock64();
+    // PDL: everything above (and the producer warp's parameter / weight streaming, which reads constants only) may overlap the
+    // tail of the tree kernel that produces idx_x / actions; wait for it before touching its outputs or the pool.  Only then
+    // may the next tree kernel start: its pre-wait section reads tree state that the kernel we waited for was still writing.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const SimIo io = io_from_desc(d);
+    stage_gather(d, io);
+    if (clk) clk[1] = clock64();
+    mbar_wait(&bar_vec, 0);          // parameters resident
+    setup_head_copies(d);
+    cta_sync();
+    infer_stages(d, io, ring, clk);
+}
+#endif  // MAZ_HMMA_NO_KERNEL
 
 }  // namespace hmma
 }  // namespace maz

@@ -91,6 +91,8 @@ extern "C" int maz_dbg_umma_gemm(const float *a, const void *w_packed, float *ou
     return 0;
 }
 
+extern "C" int maz_infer_configure(int vec_floats, int ka);
+
 extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
 {
     if (!d) return set_last_error(1, "maz_infer_recurrent: NULL descriptor");
@@ -101,12 +103,7 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
     if (d->vec_floats <= 0 || d->vec_floats % 4) return set_last_error(1, "maz_infer_recurrent: vec_floats must be a positive multiple of 4");
     const size_t dyn = fused::smem_bytes(d->KA, d->vec_floats);
     if (dyn > 227 * 1024) return set_last_error(3, "maz_infer_recurrent: parameters do not fit in shared memory");
-    static size_t configured = 0;
-    if (dyn > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused::k_recurrent_inference, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return set_last_error(2, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-        configured = dyn;
-    }
+    if (int rc = maz_infer_configure(d->vec_floats, d->KA)) return rc;
     const int roots_per_tile = 4 * (32 / d->N);
     const int tiles = (d->B + roots_per_tile - 1) / roots_per_tile;
     // programmatic dependent of the tree kernel: TMEM allocation, barrier set-up and the weight / parameter
@@ -130,6 +127,30 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
 // row-major padded layout of mazero_b200/fused.py::HmmaParams.
 extern "C" int maz_infer_small_nq(void) { return hmma::NQ; }
 
+// Opt both kernels into the device's maximum dynamic shared memory, once per device.  (cudaFuncSetAttribute SETS the limit: a
+// per-launch "raise when larger than last time" scheme lowered it when another caller had configured a smaller network in
+// between, and the next launch of the larger one failed with cudaErrorInvalidValue.)
+extern "C" int maz_infer_configure(int vec_floats, int ka)
+{
+    (void)vec_floats; (void)ka;
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_last_error(2, "no CUDA device available (libmaz_b200 has no CPU fallback)");
+    if (dev < 0 || dev >= 64 || done[dev]) return 0;
+    int optin = 227 * 1024;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, hmma::k_recurrent_inference_small);     // (the opt-in limit covers static + dynamic)
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(hmma::k_recurrent_inference_small, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fused::k_recurrent_inference);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fused::k_recurrent_inference, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return set_last_error(2, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    done[dev] = true;
+    return 0;
+}
+
 extern "C" int maz_infer_recurrent_small(const maz_infer_desc *d, void *stream)
 {
     if (!d) return set_last_error(1, "maz_infer_recurrent_small: NULL descriptor");
@@ -143,12 +164,7 @@ extern "C" int maz_infer_recurrent_small(const maz_infer_desc *d, void *stream)
             return set_last_error(1, "maz_infer_recurrent_small: bad weight chunk table");
     const size_t dyn = hmma::smem_bytes(d->vec_floats);
     if (dyn > 227 * 1024) return set_last_error(3, "maz_infer_recurrent_small: parameters do not fit in shared memory");
-    static size_t configured = 0;
-    if (dyn > configured) {
-        cudaError_t e = cudaFuncSetAttribute(hmma::k_recurrent_inference_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return set_last_error(2, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-        configured = dyn;
-    }
+    if (int rc = maz_infer_configure(d->vec_floats, d->KA)) return rc;
     const int rpt = hmma::TM / d->N;
     const int tiles = (d->B + rpt - 1) / rpt;
     // optionally a programmatic dependent of the tree kernel (MAZ_PDL bit 0): barrier set-up, the parameter copy and the first

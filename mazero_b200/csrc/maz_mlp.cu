@@ -172,7 +172,12 @@ __global__ void __launch_bounds__(NT) k_mlp_recurrent(const maz_mlp_desc d)
     for (int i = tid; i < D; i += NT) s_in[i] = d.pool[prow + i];
     for (int i = tid; i < NA; i += NT) {
         const int n = i / d.A;
-        s_in[D + i] = (d.actions[b * d.N + n] == i - n * d.A) ? 1.f : 0.f;
+        int act;
+        if (d.greedy_pool == nullptr || d.cur < 0) act = d.actions[b * d.N + n];
+        else if (n == d.cur) act = d.actions[b];                      // sequential-agent mode (mcts_sampled.py:116-147)
+        else if (n < d.cur) act = d.factor ? d.factor[b * d.N + n] : 0;
+        else act = d.greedy_pool[((size_t)(d.idx_x ? d.idx_x[b] : 0) * d.B + b) * d.N + n];
+        s_in[D + i] = (act == i - n * d.A) ? 1.f : 0.f;
     }
     __syncthreads();
     float *dyn = run_net(d.dyn, s_in, s_a, s_b, s_part, s_red);

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/maz_tree.h"
+#include "tree_host.h"
 #include "tree_kernels.cuh"
 
 using namespace maz;
@@ -57,31 +58,6 @@ struct DeviceGuard {
     }
 };
 
-struct maz_tree {
-    TreeLayout L{};
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    char *arena = nullptr;
-    size_t arena_bytes = 0;
-    float *d_lam_pow = nullptr;   // lam_pow[d], d = 0..S+1 (utils.cpp:25-26 running fp32 product)
-    float *d_logterm = nullptr;   // (float)(log((n + c_base + 1)/c_base) + c_init), n = 0..S+1
-    double *d_sqrtn = nullptr;    // sqrt((double)n)
-    float *d_pbc = nullptr;       // pb_c[n][visit] (cnode.cpp:313-314 evaluated on the host for every (n, visit))
-    int table_len = 0;
-    bool puct_set = false;
-    float c_base = 0, c_init = 0;
-    int *d_err = nullptr;
-    unsigned long long *d_sums = nullptr;
-    unsigned int seed = 0, root_offset = 0;
-    int wpb = 1;                  // warps (= trees) per block
-    size_t scratch_per_warp = 0;
-    // staging for the host-pointer entry points (allocated on first use)
-    float *s_rewards = nullptr, *s_values = nullptr, *s_probs = nullptr, *s_beta = nullptr, *s_noises = nullptr;
-    int *s_idx = nullptr;         // idx_x | idx_y | act   (B*(2+N))
-    char *s_readout = nullptr;    // device mirror of all readout arrays
-    bool prepared = false;
-};
-
 static const char *dev_err_msg(int code)
 {
     switch (code) {
@@ -92,6 +68,8 @@ static const char *dev_err_msg(int code)
         default: return "unknown device-side failure";
     }
 }
+
+namespace maz { const char *device_error_message(int code) { return dev_err_msg(code); } }
 
 static unsigned align_up(unsigned long long x, unsigned a) { return (unsigned)((x + a - 1) / a * a); }
 
@@ -174,7 +152,7 @@ int maz_tree_create_ex(maz_tree **out, int B, int N, int A, int K, int S, float 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     // one warp per tree; keep at least ~8 blocks per SM in flight before packing more trees per block
     t->wpb = (B <= sms * 8) ? 1 : (B <= sms * 16) ? 2 : 4;
-    t->scratch_per_warp = expand_scratch_bytes(N, A, K);
+    t->scratch_per_warp = tree_scratch_bytes(N, A, K);
 
     auto fail = [&](int code, const std::string &m) { maz_tree_destroy(t); return set_err(code, m); };
     cudaError_t e;

@@ -125,7 +125,8 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t z)
 // Regenerate the 624-word block in registers: lane l holds words 32c+l (c = 0..19).  Word i needs
 // word i+1 (old) and word i+397 (old, i < 227) or i-227 (new, i >= 227): all reachable with shuffles
 // whose source REGISTER index is a compile-time constant once the c-loop is unrolled.
-__device__ __forceinline__ void mt_regen(uint32_t *s, int lane)
+// (not inlined: it runs once per 624 draws, and every inlined copy is ~4 KB of code on the hot path's instruction stream)
+static __device__ __noinline__ void mt_regen(uint32_t *s, int lane)
 {
     uint32_t r[20];
 #pragma unroll
@@ -431,8 +432,63 @@ __device__ __forceinline__ void vs_scan_entry(VsScan &r, uint32_t tag, uint32_t 
         }
     }
 }
-// Apply the update given the per-lane scan.  wsum / wtot are the node's weighted_sum / tot_weight
-// (warp-uniform registers, written back by the caller).
+// The decision of SubTreeValueSet::update (utils.cpp:28-70) for ONE (node, depth) set, given its sizes and the two order
+// statistics the reference queries.  Pure per-thread arithmetic in the reference's exact fp32 operation order; wsum / wtot are
+// the node's weighted_sum / tot_weight and are updated in place.  lp = lam_pow[depth] (utils.cpp:25-26).
+struct VsDecision {
+    bool append_big;     // the new value joins the big set (else the small set)
+    int flip_pos;        // log entry whose big/small flag flips (-1: none)
+    uint32_t flip_key;   // its new key: an entry of this set is exactly tag | flag, so the flip is a plain store (a
+                         // read-modify-write of the log in global memory would stall the warp for an L2 round trip per level)
+    int err;
+};
+__device__ __forceinline__ VsDecision vs_decide(const TreeLayout &L, int cnt, int nbig, uint32_t minbig, int minpos, uint32_t maxsmall,
+                                                int maxpos, uint32_t tag, float lp, float key, float &wsum, float &wtot)
+{
+    VsDecision d;
+    d.flip_pos = -1; d.flip_key = 0; d.err = 0;
+    const int nsmall = cnt - nbig;
+    // size_lim = max(1, (int)ceil(count * (1 - quantile)))  (utils.cpp:31; float product, ceil)
+    int lim = __float2int_ru(__fmul_rn((float)(cnt + 1), L.one_minus_rho));
+    if (lim < 1) lim = 1;
+    if (nbig == lim) {       // utils.cpp:33-48
+        const float m = ord2f(minbig);
+        if (key < m) {
+            d.append_big = false;
+        } else {
+            d.flip_pos = minpos;
+            d.flip_key = tag;                     // min(big) moves to the small set
+            wsum = __fsub_rn(wsum, __fmul_rn(lp, m));
+            wtot = __fsub_rn(wtot, lp);
+            d.append_big = true;
+            wtot = __fadd_rn(wtot, lp);
+            wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
+        }
+    } else {                 // utils.cpp:49-70
+        if (nbig + 1 != lim) d.err = kErrValueSetInvariant;
+        if (nsmall == 0) {
+            d.append_big = true;
+            wtot = __fadd_rn(wtot, lp);
+            wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
+        } else {
+            const float M = ord2f(maxsmall);
+            if (key > M) {
+                d.append_big = true;
+                wtot = __fadd_rn(wtot, lp);
+                wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
+            } else {
+                d.flip_pos = maxpos;
+                d.flip_key = tag | 1u;            // max(small) moves to the big set
+                wtot = __fadd_rn(wtot, lp);
+                wsum = __fadd_rn(wsum, __fmul_rn(lp, M));
+                d.append_big = false;
+            }
+        }
+    }
+    return d;
+}
+
+// Warp-wide variant: the scan of the set is spread over the 32 lanes (root update in k_prepare).
 __device__ __forceinline__ void vs_apply(const TreeLayout &L, char *tb, int &log_len, int &err, float &wsum, float &wtot,
                                          uint32_t tag, float lp, float key, int lane, const VsScan &r)
 {
@@ -440,61 +496,21 @@ __device__ __forceinline__ void vs_apply(const TreeLayout &L, char *tb, int &log
     float *vv = f_vsval(L, tb);
     const int cnt = __reduce_add_sync(MAZ_FULL, r.cnt);
     const int nbig = __reduce_add_sync(MAZ_FULL, r.nbig);
-    const int nsmall = cnt - nbig;
-    // lp = lam_pow[depth] (utils.cpp:25-26)
-    // size_lim = max(1, (int)ceil(count * (1 - quantile)))  (utils.cpp:31; float product, ceil)
-    int lim = __float2int_ru(__fmul_rn((float)(cnt + 1), L.one_minus_rho));
-    if (lim < 1) lim = 1;
-
-    bool append_big;
-    int flip_pos = -1;       // log entry whose big/small flag flips
-    uint32_t flip_key = 0;   // its new key: an entry of this set is exactly tag | flag, so the flip is a plain store (a
-                             // read-modify-write of the log in global memory would stall the warp for an L2 round trip per level)
-    if (nbig == lim) {       // utils.cpp:33-48
-        const uint32_t gmin = __reduce_min_sync(MAZ_FULL, r.minpos >= 0 ? r.minbig : 0xffffffffu);
-        const float m = ord2f(gmin);
-        if (key < m) {
-            append_big = false;
-        } else {
-            const unsigned who = __ballot_sync(MAZ_FULL, r.minpos >= 0 && r.minbig == gmin);
-            flip_pos = __shfl_sync(MAZ_FULL, r.minpos, __ffs(who) - 1);
-            flip_key = tag;                       // min(big) moves to the small set
-            wsum = __fsub_rn(wsum, __fmul_rn(lp, m));
-            wtot = __fsub_rn(wtot, lp);
-            append_big = true;
-            wtot = __fadd_rn(wtot, lp);
-            wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
-        }
-    } else {                 // utils.cpp:49-70
-        if (nbig + 1 != lim) err = kErrValueSetInvariant;
-        if (nsmall == 0) {
-            append_big = true;
-            wtot = __fadd_rn(wtot, lp);
-            wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
-        } else {
-            const uint32_t gmax = __reduce_max_sync(MAZ_FULL, r.maxpos >= 0 ? r.maxsmall : 0u);
-            const float M = ord2f(gmax);
-            if (key > M) {
-                append_big = true;
-                wtot = __fadd_rn(wtot, lp);
-                wsum = __fadd_rn(wsum, __fmul_rn(lp, key));
-            } else {
-                const unsigned who = __ballot_sync(MAZ_FULL, r.maxpos >= 0 && r.maxsmall == gmax);
-                flip_pos = __shfl_sync(MAZ_FULL, r.maxpos, __ffs(who) - 1);
-                flip_key = tag | 1u;              // max(small) moves to the big set
-                wtot = __fadd_rn(wtot, lp);
-                wsum = __fadd_rn(wsum, __fmul_rn(lp, M));
-                append_big = false;
-            }
-        }
-    }
+    const uint32_t gmin = __reduce_min_sync(MAZ_FULL, r.minpos >= 0 ? r.minbig : 0xffffffffu);
+    const uint32_t gmax = __reduce_max_sync(MAZ_FULL, r.maxpos >= 0 ? r.maxsmall : 0u);
+    const unsigned who_min = __ballot_sync(MAZ_FULL, r.minpos >= 0 && r.minbig == gmin);
+    const unsigned who_max = __ballot_sync(MAZ_FULL, r.maxpos >= 0 && r.maxsmall == gmax);
+    const int minpos = __shfl_sync(MAZ_FULL, r.minpos, who_min ? __ffs(who_min) - 1 : 0);
+    const int maxpos = __shfl_sync(MAZ_FULL, r.maxpos, who_max ? __ffs(who_max) - 1 : 0);
+    const VsDecision d = vs_decide(L, cnt, nbig, gmin, minpos, gmax, maxpos, tag, lp, key, wsum, wtot);
+    if (d.err) err = d.err;
     if (log_len >= L.L) {
         err = kErrLogOverflow;
         return;
     }
     if (lane == 0) {
-        if (flip_pos >= 0) vk[flip_pos] = flip_key;
-        vk[log_len] = tag | (append_big ? 1u : 0u);
+        if (d.flip_pos >= 0) vk[d.flip_pos] = d.flip_key;
+        vk[log_len] = tag | (d.append_big ? 1u : 0u);
         vv[log_len] = key;
     }
     log_len += 1;

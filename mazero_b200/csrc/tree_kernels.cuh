@@ -1,7 +1,7 @@
 // tree_kernels.cuh -- the sm_100a kernels of the batched sampled-MCTS tree engine.
 // One warp per tree; blockDim.x = 32 * warps_per_block; trees are independent (no atomics).
 #pragma once
-#include "tree_device.cuh"
+#include "tree_step.cuh"
 
 namespace maz {
 
@@ -58,7 +58,7 @@ __global__ void k_prepare(TreeLayout L, char *arena, const float *__restrict__ l
     if (!warp_tree(L, tree, lane)) return;
     char *tb = arena + (size_t)tree * L.slab_bytes;
     TreeHdr *h = f_hdr(tb);
-    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
 
     int tot_nodes = 1, n_expanded = 0, log_len = 0, err = 0;
     int mt_pos = h->mt_pos;
@@ -94,144 +94,6 @@ __global__ void k_prepare(TreeLayout L, char *arena, const float *__restrict__ l
     }
 }
 
-// ---- CTree_batch::cbatch_selection -> CTree::select_path / select_child / ucb_score --------------------
-// (cnode.cpp:616-642, 381-413, 337-379, 297-335)
-// Latency-bound pointer chase: ONE memory round trip per tree level.  While the children of the current
-// node are scored, each child's own header (num_children, child_base, visit, pred_value, hidden index) is
-// already in its lane's registers, so descending is a shuffle.  The next few mt19937 outputs are
-// prefetched at kernel start (one raw draw per select_child call).
-__device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ logterm,
-                                                   const double *__restrict__ sqrtn, int table_len, float discount, int tree,
-                                                   int lane, int *__restrict__ idx_x, int *__restrict__ idx_y,
-                                                   int *__restrict__ act_out, int *g_err)
-{
-    uint16_t *path = f_path(L, tb);
-    const auto nchild = f_nchild(L, tb);
-    const auto cbase = f_cbase(L, tb);
-    const auto visit = f_visit(L, tb);
-    const auto pred_value = f_pred_value(L, tb);
-    const auto hidx = f_hidx(L, tb);
-    uint32_t *mt = f_mt(L, tb);
-
-    // round trip 0: tree header, root header, prefetched random words
-    int mt_pos = h->mt_pos;
-    const float mn = h->mm_min, mx = h->mm_max;
-    const int mmc = h->mm_cnt;
-    const RecRegs root = rec_load(L, tb, 0);
-    int C = rec_nchild(root), base = rec_cbase(root), vc = rec_visit(root);
-    float pq = rec_pred_value(root);
-    constexpr int kPre = 8;
-    uint32_t pre = 0;                          // lane l < kPre holds raw state word mt_pos + l (if in this block)
-    if (lane < kPre && mt_pos + lane < kMtN) pre = mt[mt_pos + lane];
-    int pre_used = 0;                          // draws consumed from the prefetched words
-    const int pre_avail = min(kPre, max(0, kMtN - mt_pos));
-
-    int node = 0, parent_hidx = 0, node_hidx = 0, len = 0, err = 0;
-    if (lane == 0) path[0] = 0;
-    while (C > 0) {
-        // round trip `len+1`: children fields + the children's own headers
-        float prior = 0.f, rew = 0.f, ws = 0.f, wt = 1.f, cpq = 0.f;
-        int cvis = 0, cC = 0, cbase_c = 0, chidx = -1;
-        if (lane < C) {                       // the child's whole record: two 16-byte loads, ONE round trip per level
-            const RecRegs r = rec_load(L, tb, base + lane);
-            prior = rec_prior(r);
-            cvis = rec_visit(r);
-            rew = rec_reward(r);
-            cC = rec_nchild(r);
-            cbase_c = rec_cbase(r);
-            cpq = rec_pred_value(r);
-            chidx = rec_hidx(r);
-            ws = rec_wsum(r);                 // (zero for never-visited children, unused then)
-            wt = rec_wtot(r);
-        }
-        int ci;
-        if (node == 0 && vc <= C) {
-            ci = vc - 1;  // forced root round-robin, no RNG draw (cnode.cpp:398-399)
-        } else {
-            int n = vc - 1;
-            if (n >= table_len) n = table_len - 1;
-            float score = 0.0f;
-            if (lane < C) {
-                // pb_c = log((n + c_base + 1)/c_base) + c_init   [float <- double]   (host table)
-                // pb_c *= sqrt(n) / (visit + 1)                   [float <- double product]
-                const float pb_c = (L.pbc_dim > 0)
-                                       ? L.pbc_table[(size_t)n * L.pbc_dim + min(cvis, L.pbc_dim - 1)]
-                                       : (float)__dmul_rn((double)logterm[n], __ddiv_rn(sqrtn[n], (double)(cvis + 1)));
-                const float prior_score = __fmul_rn(pb_c, prior);
-                float v = 0.0f;
-                if (cvis != 0) v = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), pq);
-                if (mmc > 0) {  // CMinMaxStats::normalize (utils.cpp:95-103)
-                    const float delta = __fsub_rn(mx, mn);
-                    const float den = (L.delta_lb < delta) ? delta : L.delta_lb;
-                    v = __fdiv_rn(__fsub_rn(v, mn), den);
-                }
-                if (v < 0.0f) v = 0.0f;
-                if (v > 1.0f) v = 1.0f;
-                score = __fadd_rn(prior_score, v);
-            }
-            // sequential epsilon-tie list of cnode.cpp:351-370, evaluated in parallel:
-            // list = {first index of the maximum} U {later indices with score >= max - 1e-6f}
-            const bool valid = (lane < C) && (score > -1000000.0f);
-            const uint32_t o = valid ? f2ord(__fadd_rn(score, 0.0f)) : 0u;
-            const uint32_t gmax = __reduce_max_sync(MAZ_FULL, o);
-            const unsigned anyvalid = __ballot_sync(MAZ_FULL, valid);
-            unsigned listmask;
-            if (anyvalid) {
-                const float M = ord2f(gmax);
-                const unsigned ismax = __ballot_sync(MAZ_FULL, valid && score == M);
-                const int istar = __ffs(ismax) - 1;
-                const float thr = __fsub_rn(M, 0.000001f);
-                listmask = __ballot_sync(MAZ_FULL, (lane < C) && (lane > istar) && (score >= thr)) | (1u << istar);
-            } else {
-                const float thr = __fsub_rn(-1000000.0f, 0.000001f);
-                listmask = __ballot_sync(MAZ_FULL, (lane < C) && (score >= thr));
-            }
-            const int nl = __popc(listmask);
-            ci = 0;
-            if (nl > 0) {  // one raw draw even for a single candidate (cnode.cpp:373-377)
-                uint32_t r;
-                if (pre_used < pre_avail) {
-                    r = mt_temper(__shfl_sync(MAZ_FULL, pre, pre_used));
-                    ++pre_used;
-                    ++mt_pos;
-                } else {
-                    r = mt_next(mt, mt_pos, lane);
-                }
-                uint32_t mrem = listmask;                   // drop the (r % nl) lowest candidates, take the next one
-                for (uint32_t skip = r % (uint32_t)nl; skip > 0; --skip) mrem &= mrem - 1;
-                ci = __ffs(mrem) - 1;
-            }
-        }
-        // descend: the chosen child's header is in lane ci's registers
-        parent_hidx = node_hidx;
-        node = base + ci;
-        node_hidx = __shfl_sync(MAZ_FULL, chidx, ci);
-        C = __shfl_sync(MAZ_FULL, cC, ci);
-        base = __shfl_sync(MAZ_FULL, cbase_c, ci);
-        vc = __shfl_sync(MAZ_FULL, cvis, ci);
-        pq = __shfl_sync(MAZ_FULL, cpq, ci);
-        ++len;
-        if (len > L.S + 1) {
-            err = kErrPathOverflow;
-            break;
-        }
-        if (lane == 0) path[len] = (uint16_t)node;
-    }
-    if (lane == 0) {
-        h->path_len = len;
-        h->mt_pos = mt_pos;
-        h->sum_path_len += len;
-        idx_x[tree] = parent_hidx;
-        idx_y[tree] = tree;
-        if (err) {
-            h->err = err;
-            *g_err = err;
-        }
-    }
-    const uint8_t *act = f_actions(L, tb) + (size_t)node * L.N;
-    for (int j = lane; j < L.N; j += 32) act_out[(size_t)tree * L.N + j] = act[j];
-}
-
 __global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ logterm, const double *__restrict__ sqrtn,
                          int table_len, float discount, int *__restrict__ idx_x, int *__restrict__ idx_y,
                          int *__restrict__ act_out, int *g_err)
@@ -242,146 +104,6 @@ __global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ lo
     select_path_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
 }
 
-// ---- CTree_batch::cbatch_expansion_and_backup -> expand_and_backprop / back_propagate ------------------
-// (cnode.cpp:644-670, 452-469, 415-450)
-// Latency plan: everything the backup needs is requested up front, in parallel with the expansion:
-//   round trip 1: tree header;   round trip 2: path[], the value log (first 256 entries, in registers),
-//   the mt19937 words of this expansion, beta / probs;   round trip 3: per-path-node fields (lane i <-> path[i]).
-// The log snapshot stays valid for the whole backup: every path node owns a distinct (slot, depth) tag, and
-// entries appended / flags flipped for one node never match another node's tag.
-constexpr int kLogRegs = 8;   // 8 x 32 log entries cached in registers; longer logs: tail scanned from memory
-
-__device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ lam_pow,
-                                                     int hidx, float discount, int K, const float *__restrict__ reward_ptr,
-                                                     const float *__restrict__ value_ptr,
-                                                     const float *__restrict__ probs, const float *__restrict__ beta,
-                                                     const ExpandScratch &sc, int lane, int *g_err, int tree = -1)
-{
-    MAZ_TS(L, tree, lane, 0);
-    griddep_launch();   // PDL: the next kernel (inference of the next simulation) may start its prologue now
-    int tot_nodes = h->tot_nodes, log_len = h->log_len, mt_pos = h->mt_pos, n_expanded = h->n_expanded, err = h->err;
-    const int len = h->path_len;
-    const int log_len0 = log_len;
-    const int leaf_eid = n_expanded;                  // expansion order the leaf is about to get
-    const uint16_t *path = f_path(L, tb);
-    const uint32_t *vk = f_vskey(L, tb);
-    const float *vv = f_vsval(L, tb);
-    const auto reward = f_reward(L, tb);
-    const auto wsum = f_wsum(L, tb);
-    const auto wtot = f_wtot(L, tb);
-
-    MAZ_TS(L, tree, lane, 1);
-    // ---- round trip 2: issue everything that depends only on the header -------------------------------------
-    const bool fast = len < 32;                       // path fits one lane per node (else: per-node loads below)
-    int my_slot = 0;
-    if (fast && lane <= len) my_slot = path[lane];
-    uint32_t lk[kLogRegs];
-    float lv[kLogRegs];
-#pragma unroll
-    for (int c = 0; c < kLogRegs; ++c) {
-        const int e = c * 32 + lane;
-        lk[c] = (e < log_len0) ? vk[e] : 0xffffffffu;   // tag 0x7fffffff<<1 never matches (slot < 65536, depth < 32768)
-        lv[c] = (e < log_len0) ? vv[e] : 0.0f;
-    }
-    const int n_draw = (L.A >= 2) ? 2 * K * L.N : 0;
-    const bool draws_pre = n_draw > 0 && n_draw <= kMtChunk && mt_pos + n_draw <= kMtN;
-    if (draws_pre) {
-        const uint32_t *mt = f_mt(L, tb);
-        for (int t = lane; t < n_draw; t += 32) sc.draws[t] = mt_temper(mt[mt_pos + t]);
-        mt_pos += n_draw;
-    }
-    const float my_lp = (fast && lane <= len) ? lam_pow[lane] : 0.f;   // lam_pow[depth], depth = lane
-    // ---- round trip 3: per-path-node fields, lane i <-> path[i] ------------------------------------------------
-    const int leaf = fast ? __shfl_sync(MAZ_FULL, my_slot, len) : (int)path[len];
-    float my_rew = 0.f, my_ws = 0.f, my_wt = 0.f, my_ppv = 0.f;
-    int my_vis = 0, my_hidx = 0;
-    if (fast && lane < len) {                         // the leaf (lane == len) is filled by the expansion below
-        const RecRegs r = rec_load(L, tb, my_slot);
-        my_rew = rec_reward(r);
-        my_ws = rec_wsum(r);
-        my_wt = rec_wtot(r);
-        my_vis = rec_visit(r);
-        my_hidx = rec_eid(r);
-    }
-    {
-        const int prev = __shfl_up_sync(MAZ_FULL, my_slot, 1);
-        if (fast && lane >= 1 && lane <= len) my_ppv = f_pred_value(L, tb)[prev];   // parent's pred_value
-    }
-
-    MAZ_TS(L, tree, lane, 2);
-    // PDL: everything above only touched this tree's own state (written by the previous tree kernel, long
-    // complete); the network outputs of THIS simulation are produced by the kernel we may be overlapping with.
-    griddep_wait();
-    const float reward_in = __ldcg(reward_ptr), value = __ldcg(value_ptr);   // L2 loads, see expand_node
-    expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, reward_in, value, probs, beta, K, 0.0f, nullptr, sc,
-                lane, draws_pre, tree);
-    MAZ_TS(L, tree, lane, 3);
-
-    // ---- back_propagate (cnode.cpp:415-450) -----------------------------------------------------------------------
-    float *qd = f_qdelta(L, tb);                      // q-delta of the e-th expanded node (the CMinMaxStats entries)
-    float G = value;
-    for (int i = len; i >= 0; --i) {
-        int slot, vis, nh;
-        float rew, ws, wt, ppv;
-        if (fast) {
-            slot = __shfl_sync(MAZ_FULL, my_slot, i);
-            rew = __shfl_sync(MAZ_FULL, my_rew, i);
-            ws = __shfl_sync(MAZ_FULL, my_ws, i);
-            wt = __shfl_sync(MAZ_FULL, my_wt, i);
-            vis = __shfl_sync(MAZ_FULL, my_vis, i);
-            nh = __shfl_sync(MAZ_FULL, my_hidx, i);
-            ppv = __shfl_sync(MAZ_FULL, my_ppv, i);
-        } else {
-            slot = path[i];
-            rew = reward[slot]; ws = wsum[slot]; wt = wtot[slot];
-            vis = f_visit(L, tb)[slot];
-            nh = f_eid(L, tb)[slot];
-            ppv = (i > 0) ? f_pred_value(L, tb)[path[i - 1]] : 0.f;
-        }
-        if (i == len) { rew = reward_in; ws = 0.f; wt = 0.f; vis = 0; nh = leaf_eid; }   // freshly expanded leaf
-        // (the reference removes the node's old q-delta from the min-max multiset here; in this layout the
-        //  entry simply lives in qd[hidden index] and is overwritten below)
-        const uint32_t tag = vs_tag(slot, len - i);
-        VsScan r;
-        vs_scan_init(r);
-#pragma unroll
-        for (int c = 0; c < kLogRegs; ++c) vs_scan_entry(r, tag, lk[c], lv[c], c * 32 + lane);
-        for (int e = kLogRegs * 32 + lane; e < log_len0; e += 32) vs_scan_entry(r, tag, vk[e], vv[e], e);
-        const float lp = fast ? __shfl_sync(MAZ_FULL, my_lp, len - i) : lam_pow[len - i];
-        vs_apply(L, tb, log_len, err, ws, wt, tag, lp, G, lane, r);
-        if (lane == 0) {
-            f_visit(L, tb)[slot] = vis + 1;
-            wsum[slot] = ws;
-            wtot[slot] = wt;
-            if (i != 0) qd[nh] = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), ppv);
-        }
-        G = __fadd_rn(rew, __fmul_rn(discount, G));
-    }
-    __syncwarp();
-    MAZ_TS(L, tree, lane, 4);
-    // CMinMaxStats min / max = reduction over the q-deltas of all visited (= expanded) non-root nodes
-    uint32_t lo = 0xffffffffu, hi = 0u;
-    for (int e = 1 + lane; e < n_expanded; e += 32) {
-        const uint32_t o = f2ord(qd[e]);
-        lo = min(lo, o);
-        hi = max(hi, o);
-    }
-    lo = __reduce_min_sync(MAZ_FULL, lo);
-    hi = __reduce_max_sync(MAZ_FULL, hi);
-    if (lane == 0) {
-        h->tot_nodes = tot_nodes;
-        h->log_len = log_len;
-        h->mt_pos = mt_pos;
-        h->n_expanded = n_expanded;
-        h->mm_cnt = n_expanded - 1;
-        h->mm_min = ord2f(lo);
-        h->mm_max = ord2f(hi);
-        h->err = err;
-        if (err) *g_err = err;
-    }
-    MAZ_TS(L, tree, lane, 5);
-}
-
 __global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restrict__ lam_pow, int hidx, float discount,
                                 int K, const float *__restrict__ rewards, const float *__restrict__ values,
                                 const float *__restrict__ probs, const float *__restrict__ beta, int *g_err)
@@ -390,10 +112,12 @@ __global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restri
     int tree, lane;
     if (!warp_tree(L, tree, lane)) return;
     char *tb = arena + (size_t)tree * L.slab_bytes;
-    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+    char *ws = smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K);
+    const ExpandScratch sc = carve_scratch(ws, L.N, L.A);
+    const LogCache lc = carve_log_cache(ws + expand_scratch_bytes(L.N, L.A, L.K));
     const size_t NA = (size_t)L.N * L.A;
     expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
-                         beta + tree * NA, sc, lane, g_err);
+                         beta + tree * NA, sc, lc, lane, g_err);
 }
 
 // ---- fused: expansion + backup of simulation s, then selection of simulation s+1 (one launch per simulation
@@ -408,10 +132,12 @@ __global__ void k_expand_backup_select(TreeLayout L, char *arena, const float *_
     int tree, lane;
     if (!warp_tree(L, tree, lane)) return;
     char *tb = arena + (size_t)tree * L.slab_bytes;
-    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+    char *ws = smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K);
+    const ExpandScratch sc = carve_scratch(ws, L.N, L.A);
+    const LogCache lc = carve_log_cache(ws + expand_scratch_bytes(L.N, L.A, L.K));
     const size_t NA = (size_t)L.N * L.A;
     expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
-                         beta + tree * NA, sc, lane, g_err, tree);
+                         beta + tree * NA, sc, lc, lane, g_err, tree);
     __syncwarp();
     select_path_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
     MAZ_TS(L, tree, lane, 6);
@@ -445,7 +171,7 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
     __syncthreads();
     if (active && role == 0) {
         // ---------------- expansion (cnode.cpp:224-295) ----------------
-        const ExpandScratch sc = carve_scratch(smem + (size_t)pair * expand_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+        const ExpandScratch sc = carve_scratch(smem + (size_t)pair * tree_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
         int tot_nodes = tot_nodes0, n_expanded = n_exp0, mt_pos = mt_pos0, err = err0;
         const int leaf = f_path(L, tb)[len];
         const int n_draw = (L.A >= 2) ? 2 * K * L.N : 0;
@@ -466,94 +192,22 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
             if (err) *g_err = err;
         }
     } else if (active) {
-        // ---------------- back_propagate (cnode.cpp:415-450) ----------------
+        // ---------------- back_propagate (cnode.cpp:415-450): the shared backup_parallel ----------------
         int log_len = log_len0, err = 0;
-        const uint16_t *path = f_path(L, tb);
-        const uint32_t *vk = f_vskey(L, tb);
-        const float *vv = f_vsval(L, tb);
-        const auto reward = f_reward(L, tb);
-    const auto wsum = f_wsum(L, tb);
-    const auto wtot = f_wtot(L, tb);
-        const bool fast = len < 32;
-        int my_slot = 0;
-        if (fast && lane <= len) my_slot = path[lane];
-        uint32_t lk[kLogRegs];
-        float lv[kLogRegs];
-#pragma unroll
-        for (int c = 0; c < kLogRegs; ++c) {
-            const int e = c * 32 + lane;
-            lk[c] = (e < log_len0) ? vk[e] : 0xffffffffu;
-            lv[c] = (e < log_len0) ? vv[e] : 0.0f;
-        }
-        const float my_lp = (fast && lane <= len) ? lam_pow[lane] : 0.f;
-        float my_rew = 0.f, my_ws = 0.f, my_wt = 0.f, my_ppv = 0.f;
-        int my_vis = 0, my_eid = 0;
-        if (fast && lane < len) {
-            const RecRegs r = rec_load(L, tb, my_slot);
-            my_rew = rec_reward(r);
-            my_ws = rec_wsum(r);
-            my_wt = rec_wtot(r);
-            my_vis = rec_visit(r);
-            my_eid = rec_eid(r);
-        }
-        {
-            const int prev = __shfl_up_sync(MAZ_FULL, my_slot, 1);
-            if (fast && lane >= 1 && lane <= len) my_ppv = f_pred_value(L, tb)[prev];
-        }
+        const LogCache lc = carve_log_cache(smem + (size_t)pair * tree_scratch_bytes(L.N, L.A, L.K) + expand_scratch_bytes(L.N, L.A, L.K));
+        log_cache_fill(L, tb, lc, 0, log_len0, lane);
         griddep_wait();
         const float reward_in = __ldcg(rewards + tree), value = __ldcg(values + tree);
-        float *qd = f_qdelta(L, tb);
-        float G = value;
-        for (int i = len; i >= 0; --i) {
-            int slot, vis, nh;
-            float rew, ws, wt, ppv;
-            if (fast) {
-                slot = __shfl_sync(MAZ_FULL, my_slot, i);
-                rew = __shfl_sync(MAZ_FULL, my_rew, i);
-                ws = __shfl_sync(MAZ_FULL, my_ws, i);
-                wt = __shfl_sync(MAZ_FULL, my_wt, i);
-                vis = __shfl_sync(MAZ_FULL, my_vis, i);
-                nh = __shfl_sync(MAZ_FULL, my_eid, i);
-                ppv = __shfl_sync(MAZ_FULL, my_ppv, i);
-            } else {
-                slot = path[i];
-                rew = reward[slot]; ws = wsum[slot]; wt = wtot[slot];
-                vis = f_visit(L, tb)[slot];
-                nh = f_eid(L, tb)[slot];
-                ppv = (i > 0) ? f_pred_value(L, tb)[path[i - 1]] : 0.f;
-            }
-            if (i == len) { rew = reward_in; ws = 0.f; wt = 0.f; vis = 0; nh = n_exp0; }   // the leaf being expanded
-            const uint32_t tag = vs_tag(slot, len - i);
-            VsScan r;
-            vs_scan_init(r);
-#pragma unroll
-            for (int c = 0; c < kLogRegs; ++c) vs_scan_entry(r, tag, lk[c], lv[c], c * 32 + lane);
-            for (int e = kLogRegs * 32 + lane; e < log_len0; e += 32) vs_scan_entry(r, tag, vk[e], vv[e], e);
-            const float lp = fast ? __shfl_sync(MAZ_FULL, my_lp, len - i) : lam_pow[len - i];
-            vs_apply(L, tb, log_len, err, ws, wt, tag, lp, G, lane, r);
-            if (lane == 0) {
-                f_visit(L, tb)[slot] = vis + 1;
-                wsum[slot] = ws;
-                wtot[slot] = wt;
-                if (i != 0) qd[nh] = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), ppv);
-            }
-            G = __fadd_rn(rew, __fmul_rn(discount, G));
-        }
         __syncwarp();
+        backup_parallel(L, tb, lam_pow, lc, f_path(L, tb), len, log_len0, n_exp0, reward_in, value, discount, lane, log_len, err);
         const int n_exp1 = n_exp0 + 1;
-        uint32_t lo = 0xffffffffu, hi = 0u;
-        for (int e = 1 + lane; e < n_exp1; e += 32) {
-            const uint32_t o = f2ord(qd[e]);
-            lo = min(lo, o);
-            hi = max(hi, o);
-        }
-        lo = __reduce_min_sync(MAZ_FULL, lo);
-        hi = __reduce_max_sync(MAZ_FULL, hi);
+        float mn, mx;
+        minmax_reduce(L, tb, n_exp1, lane, mn, mx);
         if (lane == 0) {
             h->log_len = log_len;
             h->mm_cnt = n_exp1 - 1;
-            h->mm_min = ord2f(lo);
-            h->mm_max = ord2f(hi);
+            h->mm_min = mn;
+            h->mm_max = mx;
             if (err) *g_err = err;
         }
     }

@@ -76,7 +76,23 @@ class Tree_batch:
             self._h = C.c_void_p()
             check(rc)
 
+    @classmethod
+    def from_handle(cls, handle, root_num, agent_num, action_space_size, sampled_times, simulation_num, owner=None):
+        """View of a tree batch that another native object owns (the whole-search handle of include/maz_search.h)."""
+        t = cls.__new__(cls)
+        t.root_num, t.agent_num, t.action_space_size = int(root_num), int(agent_num), int(action_space_size)
+        t.sampled_times, t.simulation_num = int(sampled_times), int(simulation_num)
+        t._h = C.c_void_p(int(handle))
+        t._cache, t._cache_dev = {}, {}
+        t._borrowed = True
+        import weakref
+
+        t._owner = None if owner is None else weakref.ref(owner)
+        return t
+
     def __del__(self):
+        if getattr(self, "_borrowed", False):
+            return
         h = getattr(self, "_h", None)
         if h and lib is not None:   # `lib` is None while the interpreter shuts down
             try:

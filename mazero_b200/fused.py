@@ -25,6 +25,7 @@ class InferDesc(C.Structure):
         ("chunk_off", C.c_uint * NCHUNK), ("chunk_bytes", C.c_uint * NCHUNK),
         ("o_bin", C.c_int), ("o_pos", C.c_int), ("o_layer", C.c_int), ("o_dyn", C.c_int), ("o_rg", C.c_int),
         ("o_vg", C.c_int), ("o_pol", C.c_int), ("dbg_clock", C.c_void_p), ("dbg_flags", C.c_int),
+        ("roots_per_tile", C.c_int), ("factor", C.c_void_p), ("greedy_pool", C.c_void_p),
     ]
 
 
@@ -194,7 +195,7 @@ class FusedParams:
             self.vec.copy_(vecf)
 
     def desc(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None, logits_out=None,
-             tree_agents=None, cur=-1, inv_tau=1.0, dbg_clock=None, small=False):
+             tree_agents=None, cur=-1, inv_tau=1.0, dbg_clock=None, small=False, factor=None, greedy_pool=None, roots_per_tile=0):
         ptr = lambda t: (t.data_ptr() if t is not None else None)
         dsc = InferDesc()
         dsc.B, dsc.N, dsc.A, dsc.KA, dsc.NAP = int(B), self.N, self.A, self.KA, self.KA
@@ -204,6 +205,7 @@ class FusedParams:
         dsc.reward, dsc.value, dsc.probs, dsc.beta = ptr(reward), ptr(value), ptr(probs), ptr(beta)
         dsc.greedy, dsc.logits_out = ptr(greedy), ptr(logits_out)
         dsc.dbg_clock = ptr(dbg_clock)
+        dsc.factor, dsc.greedy_pool, dsc.roots_per_tile = ptr(factor), ptr(greedy_pool), int(roots_per_tile)
         import os as _os
         dsc.dbg_flags = int(_os.environ.get('MAZ_DBG_FLAGS', '0'))
         dsc.wpk, dsc.vec, dsc.vec_floats = (self.wpk_h if small else self.wpk).data_ptr(), self.vec.data_ptr(), self.vec.numel()
@@ -214,6 +216,14 @@ class FusedParams:
         dsc.o_bin, dsc.o_pos, dsc.o_layer, dsc.o_dyn = o["bin"], o["pos"], o["layer"], o["dyn"]
         dsc.o_rg, dsc.o_vg, dsc.o_pol = o["rg"], o["vg"], o["pol"]
         return dsc
+
+
+def _weights_desc(self, B, small):
+    """The weight half of a descriptor (buffers NULL): what maz_search_create copies."""
+    return self.desc(B, None, None, None, None, None, None, None, None, small=small)
+
+
+FusedParams.weights_desc = _weights_desc
 
 
 # Which kernel: the tcgen05 kernel needs 128-row tiles (a CTA per 4*floor(32/N) roots), the small-batch kernel 32-row tiles

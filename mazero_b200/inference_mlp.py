@@ -36,7 +36,8 @@ class MlpDesc(C.Structure):
                 ("greedy", C.c_void_p), ("logits_out", C.c_void_p),
                 ("dyn", MlpNet), ("rew", MlpNet), ("val", MlpNet), ("pol", MlpNet),
                 ("reward_support_min", C.c_int), ("reward_support_size", C.c_int),
-                ("value_support_min", C.c_int), ("value_support_size", C.c_int)]
+                ("value_support_min", C.c_int), ("value_support_size", C.c_int),
+                ("factor", C.c_void_p), ("greedy_pool", C.c_void_p)]
 
 
 def _chain(sd, prefix):
@@ -223,8 +224,8 @@ class MlpInference:
         return NetworkOutput(*initial_inference_device(self, self.rep, observation))
 
     # ---- one launch: gather parent hidden, recurrent_inference, inverse transforms, softmax / beta ------------
-    def recurrent_fused(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None,
-                        logits_out=None, tree_agents=None, cur=-1, inv_tau=1.0, stream=None, dbg_clock=None):
+    def mlp_desc(self, B, pool=None, idx_x=None, actions=None, next_hidden=None, reward=None, value=None, probs=None, beta=None,
+                 greedy=None, logits_out=None, tree_agents=None, cur=-1, inv_tau=1.0):
         ptr = lambda t: (t.data_ptr() if t is not None else None)
         d = MlpDesc()
         d.B, d.N, d.A, d.H = int(B), self.N, self.A, self.H
@@ -236,6 +237,12 @@ class MlpInference:
         self.dyn.fill(d.dyn); self.rew.fill(d.rew); self.val.fill(d.val); self.pol.fill(d.pol)
         d.reward_support_min, d.reward_support_size = self.rsup
         d.value_support_min, d.value_support_size = self.vsup
+        return d
+
+    def recurrent_fused(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None,
+                        logits_out=None, tree_agents=None, cur=-1, inv_tau=1.0, stream=None, dbg_clock=None):
+        d = self.mlp_desc(B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy, logits_out, tree_agents, cur,
+                          inv_tau)
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         check(lib.maz_mlp_recurrent(C.byref(d), C.c_void_p(s.cuda_stream)))
 

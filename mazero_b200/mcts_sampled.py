@@ -23,8 +23,12 @@ import torch
 import ctypes as C
 import weakref
 
+import os
+from collections import OrderedDict
+
 from . import cytree, hostrng
 from ._lib import check, lib
+from .search_native import NativeSearch
 from .inference import SmacInference
 from .inference_mlp import MlpInference
 from . import inference_mlp
@@ -98,7 +102,7 @@ class _DevicePlan:
     (current_agent_idx = 0..N-1) share ONE plan -- tree arena, hidden-state pool and staging buffers are by far the
     largest allocations -- and differ only in their captured graph (`graphs[cur]`)."""
 
-    def __init__(self, inf: SmacInference, B, K, S, cur, cfg, tau, use_graph=True):
+    def __init__(self, inf: SmacInference, B, K, S, cur, cfg, tau, use_graph=True, strategy="auto"):
         self.inf, self.B, self.K, self.S, self.cur, self.tau = inf, B, K, S, cur, float(tau)
         self.N, self.A, self.H = inf.N, inf.A, inf.H
         self.joint = cur is None
@@ -106,26 +110,36 @@ class _DevicePlan:
         dev = inf.device
         self.dev = dev
         self.c_base, self.c_init, self.discount = float(cfg.pb_c_base), float(cfg.pb_c_init), float(cfg.discount)
-        self.tree = cytree.Tree_batch(B, self.Nt, self.A, K, S, float(cfg.tree_value_stat_delta_lb), 0,
-                                      float(cfg.mcts_rho), float(cfg.mcts_lambda), device=dev.index or 0)
-        self.tree.set_puct(self.c_base, self.c_init)
         f32, i32 = torch.float32, torch.int32
         D = self.N * self.H
         self.pool = torch.zeros(S + 1, B, D, dtype=f32, device=dev)          # hidden_states_pool (mcts_sampled.py:86)
-        self.greedy = torch.zeros(S + 1, B, self.N, dtype=i32, device=dev)   # argmax_a prediction(node).policy (A.11)
-        self.idx_x = torch.zeros(B, dtype=i32, device=dev)
-        self.idx_y = torch.zeros(B, dtype=i32, device=dev)
-        self.act = torch.zeros(B, self.Nt, dtype=i32, device=dev)
-        self.factor = torch.zeros(B, max(self.N, 1), dtype=i32, device=dev)
-        self.rows = torch.arange(B, dtype=torch.int64, device=dev)
         z = lambda *s: torch.zeros(*s, dtype=f32, device=dev)
-        self.root_p, self.root_b, self.root_n = z(B, self.Nt, self.A), z(B, self.Nt, self.A), z(B, self.Nt, self.A)
-        # per-simulation network outputs (fused path writes them in place)
-        self.sim_r, self.sim_v = z(B), z(B)
-        self.sim_p, self.sim_b = z(B, self.Nt, self.A), z(B, self.Nt, self.A)
-        self.graphs = {}   # current_agent_idx (or None) -> captured CUDA graph
+        self.graphs = {}   # legacy path: current_agent_idx (or None) -> captured CUDA graph
         self.use_graph = use_graph
         self.record = None  # when a list: per-simulation injected arrays are appended (parity replay tests)
+        self._rec_pending = []
+        # The product path: the whole search behind the C ABI (include/maz_search.h) -- tree arena, loop buffers, the
+        # persistent kernel / the CUDA graph all live in the library.  Only the fp32 parity mode (plain torch ops for the
+        # network, no fused kernel) keeps the loop below.
+        self.native = None
+        if getattr(inf, "fused", None) is not None and strategy != "legacy":
+            self.native = NativeSearch(inf, B, K, S, self.joint, pool=self.pool, strategy=strategy)
+            self.tree = self.native.tree
+            self.root_p, self.root_b, self.root_n = self.native.root_arrays()
+        else:
+            self.tree = cytree.Tree_batch(B, self.Nt, self.A, K, S, float(cfg.tree_value_stat_delta_lb), 0,
+                                          float(cfg.mcts_rho), float(cfg.mcts_lambda), device=dev.index or 0)
+            self.tree.set_puct(self.c_base, self.c_init)
+            self.greedy = torch.zeros(S + 1, B, self.N, dtype=i32, device=dev)   # argmax_a prediction(node).policy (A.11)
+            self.idx_x = torch.zeros(B, dtype=i32, device=dev)
+            self.idx_y = torch.zeros(B, dtype=i32, device=dev)
+            self.act = torch.zeros(B, self.Nt, dtype=i32, device=dev)
+            self.rows = torch.arange(B, dtype=torch.int64, device=dev)
+            self.root_p, self.root_b, self.root_n = z(B, self.Nt, self.A), z(B, self.Nt, self.A), z(B, self.Nt, self.A)
+            # per-simulation network outputs (fused path writes them in place)
+            self.sim_r, self.sim_v = z(B), z(B)
+            self.sim_p, self.sim_b = z(B, self.Nt, self.A), z(B, self.Nt, self.A)
+        self.factor = torch.zeros(B, max(self.N, 1), dtype=i32, device=dev)
         f64 = torch.float64
         # ---- host -> device staging: every small root input lives in ONE pinned buffer (one H2D copy per search) ----
         T = 1 if cur is None else self.N            # turns served by this plan (sequential-agent mode: one per agent)
@@ -146,6 +160,7 @@ class _DevicePlan:
                 ("marginal_priors", f32, (B, self.Nt, self.A)), ("num_children", i32, (B,)),
                 ("actions", i32, (B, K, self.Nt)), ("visit_count", i32, (B, K))]
         spec += [(f, f32, (B, K)) for f in cytree._FLOAT_FIELDS]
+        self.readout_spec = [(n, np.float32 if dt is f32 else np.int32, shp) for n, dt, shp in spec]
         words = sum(int(np.prod(shp)) for _, _, shp in spec)
         words += words & 1
         out_spec = [(f"t{t}", i32, (words,)) for t in range(T)]
@@ -170,6 +185,30 @@ class _DevicePlan:
             # the agents' chosen actions (= `factor` of the later turns) live in the result buffer: written by
             # k_agent_turn on the device, or copied from the caller's host `factor`
             self.factor = self.res["turn_actions"]
+
+    def gather_buffers(self, world):
+        """(device, pinned host) int32 buffers for the all-gather of `world` packed readout blocks."""
+        g = getattr(self, "_gather", None)
+        if g is None or g[0].numel() != world * self.out_flat.numel():
+            dev = torch.empty(world * self.out_flat.numel(), dtype=torch.int32, device=self.dev)
+            g = (dev, torch.empty(dev.numel(), dtype=torch.int32).pin_memory())
+            self._gather = g
+        return g
+
+    def device_bytes(self):
+        """HBM held by this plan (pool + arena + loop buffers + staging mirrors)."""
+        n = self.pool.numel() * 4 + self.in_flat.numel() * 4 + self.res_flat.numel() * 4
+        if self.native is not None:
+            return n + self.native.device_bytes()
+        return n + self.tree.arena_bytes() + self.greedy.numel() * 4
+
+    def close(self):
+        """Free the native objects now (cache eviction); the torch buffers go with the last reference."""
+        self.graphs.clear()
+        if self.native is not None:
+            self.native.close()
+            self.native = None
+        self.tree = None
 
     @staticmethod
     def _flat(spec, dev):
@@ -256,7 +295,10 @@ class _DevicePlan:
     # ---- host -> device staging ------------------------------------------------------------------------------
     def _stream(self):
         stream = torch.cuda.current_stream(self.dev)
-        self.tree.set_stream(stream.cuda_stream)
+        if self.native is not None:
+            self.native.set_stream(stream.cuda_stream)
+        else:
+            self.tree.set_stream(stream.cuda_stream)
         return stream
 
     def stage_roots(self, root_hidden, rewards, values, logits, legal, factor=None, cur=None):
@@ -279,8 +321,13 @@ class _DevicePlan:
         self.has_legal = legal is not None
         if legal is not None:
             put("legal", legal, (B, self.N, self.A))
-        if factor is not None and cur:
-            h["factor_in"][:, :cur] = (factor.detach().cpu().numpy() if torch.is_tensor(factor) else np.asarray(factor))[:, :cur]
+        if cur:
+            if factor is None:                       # the reference leaves zeros for the earlier agents (mcts_sampled.py:116-120)
+                h["factor_in"][:, :cur] = 0
+            else:
+                f = factor.detach().cpu().numpy() if torch.is_tensor(factor) else np.asarray(factor)
+                assert f.shape[0] == B and f.shape[1] >= cur, "factor must hold the actions of agents 0..current_agent_idx-1"
+                h["factor_in"][:, :cur] = f[:, :cur]
 
     def _apply_dev_fields(self):
         for name, t in self._dev_fields:
@@ -294,6 +341,13 @@ class _DevicePlan:
         """root preparation -> reset -> prepare -> S simulations -> readout into result slot `slot`."""
         self.cur = cur
         stream = self._stream()
+        if self.native is not None:      # ONE library call: root preparation, tree construction, S simulations, readout
+            if self.record is not None or self._rec_on:
+                self._arm_record()
+            self.native.run_dev(cur, seed, cfg, noise_eps, self.tau, self.root_r, self.root_v, self.inp["logits"],
+                                self.inp["legal"] if self.has_legal else None, self.inp[f"noise_raw{slot}"],
+                                self.factor if cur else None, self.turn_out[slot], root_index_offset=root_index_offset)
+            return
         ptr = lambda t: C.c_void_p(t.data_ptr())
         check(lib.maz_root_prepare_dev(                                         # mcts_sampled.py:57-106 on the device
             ptr(self.inp["logits"]), ptr(self.inp["legal"]) if self.has_legal else None, ptr(self.inp[f"noise_raw{slot}"]),
@@ -315,6 +369,30 @@ class _DevicePlan:
             self._loop()
         self.tree.readout_device(self.discount, self.turn_out[slot])
 
+    _rec_on = False
+
+    def _arm_record(self):
+        """Parity instrumentation of the native search: per-simulation selections + injected network outputs."""
+        if self.record is None:
+            self.native.set_record(None)
+            self._rec_on = False
+            return
+        S, B, Nt, A, dev = self.S, self.B, self.Nt, self.A, self.dev
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        i = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+        rec = {"rewards": f(S, B), "values": f(S, B), "probs": f(S, B, Nt, A), "beta": f(S, B, Nt, A), "idx_x": i(S, B),
+               "actions": i(S, B, Nt)}
+        self.native.set_record(rec)
+        self._rec_on = True
+        self._rec_pending.append(rec)
+
+    def _flush_record(self):
+        for rec in self._rec_pending:
+            for s in range(self.S):
+                self.record.append((rec["rewards"][s], rec["values"][s], rec["probs"][s], rec["beta"][s], rec["idx_x"][s],
+                                    rec["actions"][s]))
+        self._rec_pending = []
+
     def run(self, seed, cfg, noise_eps, noise_raw, root_index_offset=0, cur=None):
         """One search after `stage_roots`: `noise_raw` (B,Nt,A) are the raw Dirichlet draws (host).  Returns the
         padded readout dict (host numpy)."""
@@ -328,7 +406,20 @@ class _DevicePlan:
         self._enqueue_search(0, cur, seed, cfg, noise_eps, root_index_offset)
         self.out_host.copy_(self.out_flat, non_blocking=True)
         self.tree.check()          # synchronises the stream and surfaces device-side invariant failures
+        if self._rec_pending:
+            self._flush_record()
         return {k: v.copy() for k, v in self.out_np.items()}
+
+    def enqueue(self, seed, cfg, noise_eps, noise_raw, root_index_offset=0, cur=None):
+        """`run` without the device -> host copy and without synchronising: the readouts stay in `out_flat` (device)."""
+        assert (cur is None) == self.joint, "a plan is either joint or sequential"
+        self._stream()
+        self.inp_np["noise_raw0"][:] = noise_raw
+        self._h2d(0, self.in_turn[0][1])
+        self._apply_dev_fields()
+        if cur:
+            self.factor[:, :cur].copy_(self.inp["factor_in"][:, :cur], non_blocking=True)
+        self._enqueue_search(0, cur, seed, cfg, noise_eps, root_index_offset)
 
     # ---- the N sequential-agent turns of one environment step, back to back on the device -------------------------
     def begin_turns(self):
@@ -362,6 +453,8 @@ class _DevicePlan:
     def finish_turns(self):
         self.res_host.copy_(self.res_flat, non_blocking=True)      # ONE D2H copy for all turns
         self.tree.check()
+        if self._rec_pending:
+            self._flush_record()
         r = self.res_np
         outs = [{k: v.copy() for k, v in d.items()} for d in self.turn_out_np]
         return (outs, r["turn_actions"].copy(), r["policy_dist"].copy(), r["prob_prod"].copy(), r["entropy"].copy())
@@ -386,21 +479,57 @@ class _DevicePlan:
 
 # The workers build a NEW `SampledMCTS(config, np_random)` for every environment step / every agent
 # (selfplay_worker.py:191, reanalyze_worker.py:284), so the expensive device objects -- packed weights, tree arena,
-# hidden-state pool, captured CUDA graphs -- are cached per PROCESS, not per instance: keyed by the model object and
-# the problem shape / search constants.  An instance's `_inference` / `_plans` list what that instance used.
-_INFERENCE_CACHE = {}   # (id(model), device) -> (weakref to the model, SmacInference | MlpInference)
-_PLAN_CACHE = {}        # (id(inference), B, K, S, joint, tau, search constants, use_graph) -> _DevicePlan
+# hidden-state pool, CUDA graphs -- are cached per PROCESS, not per instance: keyed by the model object and the problem
+# shape / search constants.  Both caches are bounded: plans by a byte budget with least-recently-used eviction (a reanalyze
+# worker whose batch size varies would otherwise keep one arena + pool per size), inference objects by the life of their
+# model (weak reference + finalizer).
+_INFERENCE_CACHE = {}          # (id(model), device, mode) -> (weakref to the model, SmacInference | MlpInference)
+_PLAN_CACHE = OrderedDict()    # plan key -> _DevicePlan, least recently used first
+PLAN_CACHE_BYTES = int(float(os.environ.get("MAZ_PLAN_CACHE_GB", "32")) * (1 << 30))
+
+
+def _plan_cache_bytes():
+    return sum(p.device_bytes() for p in _PLAN_CACHE.values())
+
+
+def _plan_cache_put(key, plan):
+    _PLAN_CACHE[key] = plan
+    _PLAN_CACHE.move_to_end(key)
+    # evict least recently used plans until the budget holds; the plan just inserted always stays
+    while len(_PLAN_CACHE) > 1 and _plan_cache_bytes() > PLAN_CACHE_BYTES:
+        _, old = _PLAN_CACHE.popitem(last=False)
+        old.close()            # frees the arena / loop buffers now, not when the last Python reference dies
+
+
+def _drop_inference(key):
+    hit = _INFERENCE_CACHE.pop(key, None)
+    if hit is None:
+        return
+    inf = hit[1]
+    for k in [k for k, p in _PLAN_CACHE.items() if p.inf is inf]:
+        _PLAN_CACHE.pop(k).close()
 
 
 def clear_caches():
     """Drop every cached device object (arenas, pools, graphs) of this process."""
+    for p in _PLAN_CACHE.values():
+        p.close()
     _INFERENCE_CACHE.clear()
     _PLAN_CACHE.clear()
 
 
+def _weights_signature(tensors):
+    """Cheap change detector of a module's parameters: in-place updates bump `_version`, re-assigned storages
+    (`param.data = ...`, load_state_dict(assign=True)) change `data_ptr`."""
+    v = 0
+    for t in tensors:
+        v = (v * 1000003 + int(t._version) * 8191 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+    return v
+
+
 class SampledMCTS(object):
     def __init__(self, config, np_random: np.random.RandomState = None, use_cuda_graph: bool = True,
-                 inference_mode: str = "auto", speculate_noise: bool = True):
+                 inference_mode: str = "auto", speculate_noise: bool = True, search_strategy: str = "auto"):
         """inference_mode: "bf16" = fused tensor-core kernel, "fp32" = parity mode (plain fp32 torch ops on the
         device), "auto" = bf16 when the network has the reference SMAC architecture, else fp32.
         speculate_noise: draw the NEXT search's exploration noise on a background thread while the GPU runs the current
@@ -410,6 +539,9 @@ class SampledMCTS(object):
         self.np_random = np.random if np_random is None else np_random
         self.use_cuda_graph = use_cuda_graph
         self.inference_mode = inference_mode
+        # "auto" | "persistent" | "graph": how the library runs the loop (include/maz_search.h); "legacy": the round-1 Python /
+        # torch.cuda.CUDAGraph loop over the per-step C ABI (kept as a cross-check of the native search)
+        self.search_strategy = search_strategy
         self._inference = {}
         self._plans = {}
 
@@ -419,6 +551,20 @@ class SampledMCTS(object):
             return model
         if not isinstance(model, torch.nn.Module):
             return None
+        # fast path: this model object was adapted before -- no state_dict() walk, only the change signature of its tensors
+        probe = getattr(model, "_maz_inference", None)
+        if probe is not None:
+            dev_s = str(torch.device(device)) if device is not None else probe.get("default_dev")
+            key = (id(model), dev_s, self.inference_mode)
+            hit = _INFERENCE_CACHE.get(key)
+            if hit is not None and hit[0]() is model:
+                inf = hit[1]
+                sig = _weights_signature(inf._src_tensors)
+                if sig != inf._src_signature:                 # weights were updated (set_weights / load_state_dict)
+                    inf.refresh(model.state_dict())
+                    inf._src_signature = sig
+                self._inference[key] = inf
+                return inf
         try:
             sd = model.state_dict()
         except Exception:
@@ -430,13 +576,13 @@ class SampledMCTS(object):
         dev = torch.device(device) if device is not None else sd["prediction_network.fc_policy.0.weight"].device
         if dev.type != "cuda":
             return None
-        key = (id(model), str(dev))
+        key = (id(model), str(dev), self.inference_mode)      # "fp32" parity mode must never be served a cached bf16 object
         hit = _INFERENCE_CACHE.get(key)
         inf = hit[1] if hit is not None and hit[0]() is model else None      # (ids are reused after garbage collection)
-        version = sum(int(getattr(p, "_version", 0)) for p in sd.values())
+        if inf is None and hit is not None:
+            _drop_inference(key)
         if inf is None and mlp:
-            inf = MlpInference.from_model(model, device=dev, mode="torch" if self.inference_mode == "torch" else "fp32")
-            inf._src_version = version
+            inf = MlpInference.from_model(model, device=dev, mode="torch" if self.inference_mode in ("torch", "fp32torch") else "fp32")
         elif inf is None:
             mode = self.inference_mode
             if mode == "auto":
@@ -445,11 +591,19 @@ class SampledMCTS(object):
                 h = int(getattr(model, "hidden_state_size_per_agent", getattr(model, "hidden", 128)))
                 mode = "bf16" if fused.supported(sd, int(model.num_agents), int(model.action_space_size), h) else "fp32"
             inf = SmacInference.from_model(model, device=dev, mode=mode)
-            inf._src_version = version
-        elif getattr(inf, "_src_version", None) != version:   # weights were updated in place (set_weights)
+        else:
             inf.refresh(sd)
-            inf._src_version = version
-        _INFERENCE_CACHE[key] = (weakref.ref(model), inf)
+        inf._src_tensors = list(model.parameters()) + list(model.buffers())
+        inf._src_signature = _weights_signature(inf._src_tensors)
+        if hit is None or hit[1] is not inf:
+            _INFERENCE_CACHE[key] = (weakref.ref(model), inf)
+            weakref.finalize(model, _drop_inference, key)     # a dead model releases its packed weights and its plans
+        try:
+            marks = getattr(model, "_maz_inference", None) or {}
+            marks["default_dev"] = str(dev) if device is None else marks.get("default_dev")
+            model._maz_inference = marks
+        except Exception:
+            pass
         self._inference[key] = inf
         return inf
 
@@ -535,17 +689,68 @@ class SampledMCTS(object):
         return self._search_step_path(model, network_output, current_agent_idx, factor, true_num_agents, device, sampled_tau,
                                       seed, noise_epsilon, batch_rewards, batch_values, probs, beta, noises, root_index_offset)
 
+    # ---- roots sharded over the ranks of a process group, ONE exchange per search ------------------------------
+    def batch_search_sharded(self, model, network_output, current_agent_idx, factor, true_num_agents, total_roots: int,
+                             legal_actions_lst=None, device=None, add_noise: bool = False, sampled_tau: float = 1.0, group=None,
+                             gather: bool = True) -> SearchOutput:
+        """`batch_search` for a batch of `total_roots` roots split over the ranks of `group` (torch.distributed, NCCL): this rank
+        passes ITS contiguous slice `sharding.shard_range(total_roots, rank, world)` of every per-root argument, searches it with
+        the trees seeded by their GLOBAL root index (results do not depend on the number of ranks, cnode.cpp:574), and ONE
+        all-gather of the packed readouts (device tensors, NCCL over NVLink) gives every rank the SearchOutput of all roots.
+        Every rank must hold `np_random` in the same state (the noise of ALL roots and the tree seed are drawn on every rank, as
+        the single-process reference would, and sliced).  gather=False returns the local slice only (no collective)."""
+        import torch.distributed as dist
+
+        from . import sharding
+
+        cfg = self.config
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        start, count = sharding.shard_range(total_roots, rank, world)
+        Bp = sharding.shard_range(total_roots, 0, world)[1]               # the largest shard: every rank searches Bp roots
+        joint = current_agent_idx is None
+        A, Nt = cfg.action_space_size, (true_num_agents if joint else 1)
+        if network_output.hidden_state.shape[0] != count:
+            raise ValueError(f"rank {rank}: expected {count} local roots, got {network_output.hidden_state.shape[0]}")
+        inf = self._device_inference(model, device)
+        if inf is None:
+            raise RuntimeError("batch_search_sharded needs a network with a device path (SMAC / matrix MAMuZeroNet on a CUDA device)")
+        pad = lambda x: None if x is None else sharding.pad_rows(x, Bp)
+        plan = self._plan(inf, Bp, current_agent_idx, sampled_tau)
+        plan.stage_roots(pad(network_output.hidden_state), pad(network_output.reward), pad(network_output.value),
+                         pad(network_output.policy_logits), pad(legal_actions_lst), pad(factor), current_agent_idx)
+        noises = hostrng.dirichlet_f32(self.np_random, cfg.root_dirichlet_alpha, A, total_roots * Nt).reshape(total_roots, Nt, A)
+        seed = self.np_random.choice(256)
+        plan.enqueue(int(seed), cfg, cfg.root_exploration_fraction if add_noise else 0.0, pad(noises[start:start + count]),
+                     root_index_offset=start, cur=current_agent_idx)
+        if not gather or world == 1:
+            plan.out_host.copy_(plan.out_flat, non_blocking=True)
+            plan.tree.check()
+            r = {k: v[:count].copy() for k, v in plan.out_np.items()}
+            return _output_from_readout(r)
+        gbuf, ghost = plan.gather_buffers(world)
+        dist.all_gather_into_tensor(gbuf, plan.out_flat, group=group)                # the one collective of the search
+        ghost.copy_(gbuf, non_blocking=True)
+        plan.tree.check()
+        blocks = ghost.numpy().reshape(world, -1)
+        return _output_from_readout(sharding.merge_shards(blocks, plan.readout_spec, total_roots, world))
+
     def _plan(self, inf, B, current_agent_idx, sampled_tau) -> _DevicePlan:
         cfg = self.config
+        # The native search takes every search constant per call (its CUDA graphs are keyed by them inside the library), so a
+        # plan depends on the shape only; the legacy loop freezes the constants into its captured graphs: they are in its key.
         key = (id(inf), B, cfg.sampled_action_times, cfg.num_simulations, current_agent_idx is None, float(sampled_tau),
-               float(cfg.pb_c_base), float(cfg.pb_c_init), float(cfg.discount), bool(self.use_cuda_graph))
+               self.search_strategy)
+        if self.search_strategy == "legacy" or getattr(inf, "fused", None) is None:
+            key += (float(cfg.pb_c_base), float(cfg.pb_c_init), float(cfg.discount), float(cfg.tree_value_stat_delta_lb),
+                    float(cfg.mcts_rho), float(cfg.mcts_lambda), bool(self.use_cuda_graph))
         plan = _PLAN_CACHE.get(key)                                                  # all sequential turns share a plan
-        if plan is not None and plan.inf is not inf:
+        if plan is not None and (plan.inf is not inf or plan.tree is None):
             plan = None
         if plan is None:
             plan = _DevicePlan(inf, B, cfg.sampled_action_times, cfg.num_simulations, current_agent_idx, cfg, sampled_tau,
-                               self.use_cuda_graph)
-            _PLAN_CACHE[key] = plan
+                               self.use_cuda_graph, strategy=self.search_strategy)
+        plan.c_base, plan.c_init, plan.discount = float(cfg.pb_c_base), float(cfg.pb_c_init), float(cfg.discount)
+        _plan_cache_put(key, plan)
         self._plans[key] = plan
         return plan
 

@@ -57,3 +57,36 @@ def all_gather_readouts(readout, total_roots, group=None, device=None):
     dist.all_gather(parts, buf, group=group)
     rows = [parts[r][: shard_range(total_roots, r, world)[1]].cpu().numpy() for r in range(world)]
     return unpack_readout(np.concatenate(rows, axis=0), layout)
+
+
+# ---- the product-level sharded search: device tensors end to end ------------------------------------------------------------
+def pad_rows(x, rows):
+    """Repeat the last row of a per-root array (numpy or torch) up to `rows` rows: ranks with one root less than the largest shard
+    search a dummy copy of their last root, whose results are dropped after the exchange."""
+    n = x.shape[0]
+    if n == rows:
+        return x
+    if torch.is_tensor(x):
+        return torch.cat([x, x[-1:].expand(rows - n, *x.shape[1:])], dim=0)
+    return np.concatenate([x, np.repeat(x[-1:], rows - n, axis=0)], axis=0)
+
+
+def split_packed(words, spec, roots):
+    """One rank's packed readout block (1-D int32, field-major as `_DevicePlan` lays it out) -> dict of per-root arrays."""
+    out, o = {}, 0
+    for name, dt, shp in spec:
+        n = int(np.prod(shp))
+        out[name] = words[o:o + n].view(dt).reshape(shp)
+        o += n
+    assert all(v.shape[0] == roots for v in out.values())
+    return out
+
+
+def merge_shards(blocks, spec_of, total_roots, world):
+    """blocks[r] = rank r's packed readouts (padded to the largest shard); returns the dict for ALL roots in global order."""
+    parts = []
+    for r in range(world):
+        _, count = shard_range(total_roots, r, world)
+        d = split_packed(blocks[r], spec_of, shard_range(total_roots, 0, world)[1])
+        parts.append({k: v[:count] for k, v in d.items()})
+    return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}

@@ -205,7 +205,7 @@ def test_sequential_turns_share_one_plan_without_leaking_state(built_lib):
         looped.append(shared.batch_search(inf, out0, cur, factor, N, None, "cuda:0", add_noise=True))
     assert len(shared._plans) == 1
     plan = next(iter(shared._plans.values()))
-    assert sorted(plan.graphs) == [0, 1, 2]
+    assert plan.native is not None or sorted(plan.graphs) == [0, 1, 2]     # (the native search keeps its graphs in the library)
     fresh = SampledMCTS(cfg, np.random.RandomState(101)).batch_search(inf, out0, 1, factor, N, None, "cuda:0", add_noise=True)
     for o in (looped[1], looped[3]):
         assert np.array_equal(o.value, fresh.value)
@@ -234,12 +234,20 @@ def test_new_instances_reuse_the_cached_device_objects(built_lib):
     assert next(iter(first._inference.values())) is next(iter(second._inference.values()))
     assert np.array_equal(r1.value, r2.value) and np.array_equal(r1.marginal_visit_count, r2.marginal_visit_count)
     assert r1.sampled_qvalues == r2.sampled_qvalues
-    # another configuration of the search constants does not share the plan
+    # another configuration of the search constants: the native search takes them per call (its graphs are keyed by them inside
+    # the library), so the plan IS shared and the new constants take effect (tests/test_search_native_gpu.py)
     cfg2 = MockConfig(N, A, S, K)
     cfg2.discount = 0.9
     third = SampledMCTS(cfg2, np.random.RandomState(3))
-    third.batch_search(model, out0, 1, None, N, None, torch.device("cuda:0"), add_noise=True)
-    assert next(iter(third._plans.values())) is not next(iter(first._plans.values()))
+    r3 = third.batch_search(model, out0, 1, None, N, None, torch.device("cuda:0"), add_noise=True)
+    assert next(iter(third._plans.values())) is next(iter(first._plans.values()))
+    assert not all(np.array_equal(a, b) for a, b in zip(r3.sampled_qvalues, r1.sampled_qvalues))
+    # another batch size does not
+    out1 = out0._replace(hidden_state=out0.hidden_state[:B - 1], reward=out0.reward[:B - 1], value=out0.value[:B - 1],
+                         policy_logits=out0.policy_logits[:B - 1])
+    fourth = SampledMCTS(cfg, np.random.RandomState(3))
+    fourth.batch_search(model, out1, 1, None, N, None, torch.device("cuda:0"), add_noise=True)
+    assert next(iter(fourth._plans.values())) is not next(iter(first._plans.values()))
     n = len(mcts_sampled._PLAN_CACHE)
     mcts_sampled.clear_caches()
     assert n >= 2 and not mcts_sampled._PLAN_CACHE
