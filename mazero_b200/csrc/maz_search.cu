@@ -148,7 +148,7 @@ int maz_search_create(maz_search **out, const maz_search_config *cfg)
     const int rpt_env = env_int("MAZ_SEARCH_RPT", 0);
     if (rpt_env > 0 && rpt_env < rpt) rpt = rpt_env;
     bool persist_ok = cfg->net_kind == MAZ_NET_SMAC && N <= hmma::TM && rpt >= 1 &&
-                      (size_t)rpt * tree_scratch_bytes(s->Nt, A, K) <= persist::TREE_SCRATCH_BYTES &&
+                      (size_t)rpt * tree_scratch_bytes(s->Nt, A, K, S) <= persist::TREE_SCRATCH_BYTES &&
                       hmma::smem_bytes(s->sm.vec_floats) <= 227 * 1024;
     if (strat == MAZ_SEARCH_PERSISTENT && !persist_ok) {
         set_last_error(MAZ_ERR_UNSUPPORTED, "maz_search_create: the persistent kernel does not support this network / shape");

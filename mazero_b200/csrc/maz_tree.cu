@@ -100,6 +100,13 @@ static int build_layout(TreeLayout &L, int B, int N, int A, int K, int S, float 
     L.off_path = take(2ull * (S + 4));
     L.off_vskey = take(4ull * L.L);
     L.off_vsval = take(4ull * L.L);
+    L.off_depth = take(2ull * (S + 4));      // depth of the e-th expanded node (its distance from the root)
+    {   // wide selection: worth it once the sequential descent (~2 k cycles per level) costs more than one pass over all expanded
+        // nodes (~4 k cycles per 32 of them).  MAZ_SELECT_WIDE=0 never, 1 always (tests run both: identical results).
+        const char *e = getenv("MAZ_SELECT_WIDE");
+        const int chunks = (S + 1 + 31) / 32;
+        L.wide_min_len = e ? (atoi(e) ? 0 : 1 << 30) : 2 + 2 * chunks;
+    }
     L.slab_bytes = align_up(o, 256);
     if (o > 0xfffffff0ull) return set_err(MAZ_ERR_UNSUPPORTED, "per-tree slab exceeds 4 GiB");
     return MAZ_OK;
@@ -152,7 +159,7 @@ int maz_tree_create_ex(maz_tree **out, int B, int N, int A, int K, int S, float 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     // one warp per tree; keep at least ~8 blocks per SM in flight before packing more trees per block
     t->wpb = (B <= sms * 8) ? 1 : (B <= sms * 16) ? 2 : 4;
-    t->scratch_per_warp = tree_scratch_bytes(N, A, K);
+    t->scratch_per_warp = tree_scratch_bytes(N, A, K, S);
 
     auto fail = [&](int code, const std::string &m) { maz_tree_destroy(t); return set_err(code, m); };
     cudaError_t e;

@@ -78,9 +78,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_search_persistent(const __grid_
     const bool has_tree = warp < rpt && tree < d.B;
     char *tb = P.arena + (size_t)(has_tree ? tree : 0) * L.slab_bytes;
     const size_t B = (size_t)d.B, NA = (size_t)L.N * L.A;
-    char *wscr = reinterpret_cast<char *>(hsm) + TREE_SCRATCH_OFF + (size_t)warp * tree_scratch_bytes(L.N, L.A, L.K);
-    const ExpandScratch sc = carve_scratch(wscr, L.N, L.A);
-    const LogCache lc = carve_log_cache(wscr + expand_scratch_bytes(L.N, L.A, L.K));
+    const StepScratch scr = carve_step_scratch(reinterpret_cast<char *>(hsm) + TREE_SCRATCH_OFF + (size_t)warp * tree_scratch_bytes(L.N, L.A, L.K, L.S),
+                                               L.N, L.A, L.K, L.S);
     long long *clk = (P.tree_clock != nullptr && blockIdx.x == 0 && tid == 0) ? P.tree_clock : nullptr;
     long long *cta_clk = (P.tree_clock != nullptr && tid == 0) ? P.tree_clock + 2 * P.S + 4 * blockIdx.x : nullptr;
     const long long k0 = cta_clk ? clock64() : 0;
@@ -106,12 +105,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_search_persistent(const __grid_
             const long long q0 = tree_clk ? clock64() : 0;
             if (s > 0)
                 expand_backup_device(L, tb, f_hdr(tb), P.lam_pow, s, P.discount, P.K, io.reward + tree, io.value + tree,
-                                     io.probs + (size_t)tree * NA, io.beta + (size_t)tree * NA, sc, lc, lane, P.g_err);
+                                     io.probs + (size_t)tree * NA, io.beta + (size_t)tree * NA, scr, lane, P.g_err);
             __syncwarp();
             const long long q1 = tree_clk ? clock64() : 0;
             if (s < P.S) {
                 const size_t rn = P.rec ? (size_t)s : 0;
-                select_path_device(L, tb, f_hdr(tb), P.logterm, P.sqrtn, P.table_len, P.discount, tree, lane,
+                select_next_device(L, tb, f_hdr(tb), P.logterm, P.sqrtn, P.table_len, P.discount, tree, lane, &scr,
                                    const_cast<int *>(d.idx_x) + rn * B, P.idx_y, const_cast<int *>(d.actions) + rn * B * L.N, P.g_err);
             }
             if (tree_clk) {

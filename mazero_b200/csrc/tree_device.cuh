@@ -33,6 +33,7 @@ MAZ_FIELD(uint16_t, f_expslot, off_expslot)
 MAZ_FIELD(uint16_t, f_path, off_path)
 MAZ_FIELD(uint32_t, f_vskey, off_vskey)
 MAZ_FIELD(float, f_vsval, off_vsval)
+MAZ_FIELD(uint16_t, f_depth, off_depth)
 #undef MAZ_FIELD
 
 // one field of the node records, indexed by slot (the cold paths keep the array notation; the hot paths load whole records)
@@ -250,7 +251,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
                                            const float *__restrict__ probs, const float *__restrict__ beta,
                                            int K, float eps, const float *__restrict__ noises,
                                            const ExpandScratch &sc, int lane, bool draws_prefetched = false, int dbg_tree = -1,
-                                           bool init_stats = true)
+                                           bool init_stats = true, int depth = 0)
 {
     const int N = L.N, A = L.A, NA = N * A;
 
@@ -399,6 +400,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
             f_wtot(L, tb)[slot] = 0.0f;
         }
         f_expslot(L, tb)[n_expanded] = (uint16_t)slot;
+        f_depth(L, tb)[n_expanded] = (uint16_t)depth;
         f_eid(L, tb)[slot] = (uint16_t)n_expanded;   // expansion order: index of this node's q-delta entry
     }
     tot_nodes = base + C;

@@ -58,7 +58,7 @@ __global__ void k_prepare(TreeLayout L, char *arena, const float *__restrict__ l
     if (!warp_tree(L, tree, lane)) return;
     char *tb = arena + (size_t)tree * L.slab_bytes;
     TreeHdr *h = f_hdr(tb);
-    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+    const ExpandScratch sc = carve_scratch(smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K, L.S), L.N, L.A);
 
     int tot_nodes = 1, n_expanded = 0, log_len = 0, err = 0;
     int mt_pos = h->mt_pos;
@@ -112,12 +112,10 @@ __global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restri
     int tree, lane;
     if (!warp_tree(L, tree, lane)) return;
     char *tb = arena + (size_t)tree * L.slab_bytes;
-    char *ws = smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K);
-    const ExpandScratch sc = carve_scratch(ws, L.N, L.A);
-    const LogCache lc = carve_log_cache(ws + expand_scratch_bytes(L.N, L.A, L.K));
+    const StepScratch scr = carve_step_scratch(smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K, L.S), L.N, L.A, L.K, L.S);
     const size_t NA = (size_t)L.N * L.A;
     expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
-                         beta + tree * NA, sc, lc, lane, g_err);
+                         beta + tree * NA, scr, lane, g_err);
 }
 
 // ---- fused: expansion + backup of simulation s, then selection of simulation s+1 (one launch per simulation
@@ -132,14 +130,12 @@ __global__ void k_expand_backup_select(TreeLayout L, char *arena, const float *_
     int tree, lane;
     if (!warp_tree(L, tree, lane)) return;
     char *tb = arena + (size_t)tree * L.slab_bytes;
-    char *ws = smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K);
-    const ExpandScratch sc = carve_scratch(ws, L.N, L.A);
-    const LogCache lc = carve_log_cache(ws + expand_scratch_bytes(L.N, L.A, L.K));
+    const StepScratch scr = carve_step_scratch(smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K, L.S), L.N, L.A, L.K, L.S);
     const size_t NA = (size_t)L.N * L.A;
     expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
-                         beta + tree * NA, sc, lc, lane, g_err, tree);
+                         beta + tree * NA, scr, lane, g_err, tree);
     __syncwarp();
-    select_path_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
+    select_next_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, &scr, idx_x, idx_y, act_out, g_err);
     MAZ_TS(L, tree, lane, 6);
 }
 
@@ -158,6 +154,7 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
     const int pair = warp >> 1, role = warp & 1;              // role 0: expansion (+ selection), role 1: backup
     const int tree = blockIdx.x * (blockDim.x >> 6) + pair;
     const bool active = tree < L.B;
+    const StepScratch scr = carve_step_scratch(smem + (size_t)pair * tree_scratch_bytes(L.N, L.A, L.K, L.S), L.N, L.A, L.K, L.S);
     char *tb = arena + (size_t)(active ? tree : 0) * L.slab_bytes;
     TreeHdr *h = f_hdr(tb);
     const size_t NA = (size_t)L.N * L.A;
@@ -171,7 +168,7 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
     __syncthreads();
     if (active && role == 0) {
         // ---------------- expansion (cnode.cpp:224-295) ----------------
-        const ExpandScratch sc = carve_scratch(smem + (size_t)pair * tree_scratch_bytes(L.N, L.A, L.K), L.N, L.A);
+        const ExpandScratch sc = scr.ex;
         int tot_nodes = tot_nodes0, n_expanded = n_exp0, mt_pos = mt_pos0, err = err0;
         const int leaf = f_path(L, tb)[len];
         const int n_draw = (L.A >= 2) ? 2 * K * L.N : 0;
@@ -183,7 +180,7 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
         }
         griddep_wait();
         expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, __ldcg(rewards + tree), __ldcg(values + tree),
-                    probs + tree * NA, beta + tree * NA, K, 0.0f, nullptr, sc, lane, draws_pre, -1, /*init_stats=*/false);
+                    probs + tree * NA, beta + tree * NA, K, 0.0f, nullptr, sc, lane, draws_pre, -1, /*init_stats=*/false, /*depth=*/len);
         if (lane == 0) {
             h->tot_nodes = tot_nodes;
             h->mt_pos = mt_pos;
@@ -194,12 +191,11 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
     } else if (active) {
         // ---------------- back_propagate (cnode.cpp:415-450): the shared backup_parallel ----------------
         int log_len = log_len0, err = 0;
-        const LogCache lc = carve_log_cache(smem + (size_t)pair * tree_scratch_bytes(L.N, L.A, L.K) + expand_scratch_bytes(L.N, L.A, L.K));
-        log_cache_fill(L, tb, lc, 0, log_len0, lane);
+        LogRegs lr;
+        log_prefetch(L, tb, log_len0, lane, lr);
         griddep_wait();
         const float reward_in = __ldcg(rewards + tree), value = __ldcg(values + tree);
-        __syncwarp();
-        backup_parallel(L, tb, lam_pow, lc, f_path(L, tb), len, log_len0, n_exp0, reward_in, value, discount, lane, log_len, err);
+        backup_parallel(L, tb, lam_pow, scr, lr, f_path(L, tb), len, log_len0, n_exp0, reward_in, value, discount, lane, log_len, err);
         const int n_exp1 = n_exp0 + 1;
         float mn, mx;
         minmax_reduce(L, tb, n_exp1, lane, mn, mx);
@@ -215,7 +211,7 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
     __syncthreads();   // expansion and backup of every tree of the block are complete and visible
     const long long t2 = dbg ? clock64() : 0;
     if (active && role == 0)
-        select_path_device(L, tb, h, logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
+        select_next_device(L, tb, h, logterm, sqrtn, table_len, discount, tree, lane, &scr, idx_x, idx_y, act_out, g_err);
     if (dbg && role == 0) {
         dbg[2] = clock64() - t2;
         dbg[3] = len;

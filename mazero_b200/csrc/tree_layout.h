@@ -63,9 +63,11 @@ struct TreeLayout {
     long long *dbg_clock;   // profiling only (NULL): SM-cycle timestamps of tree 0's phases, 64 entries
     const float *pbc_table; // pb_c[n][visit] = (float)((double)logterm[n] * (sqrt((double)n) / (double)(visit + 1))), host-built
     int pbc_dim;            // table is pbc_dim x pbc_dim (0: compute on the device with fp64)
+    int wide_min_len;       // selection: use the all-expanded-nodes-in-parallel form when the previous path was at least this long
+                            // (0 = always when possible, large = never); both forms give identical results
     // byte offsets inside a slab (all multiples of 128)
     unsigned off_mt, off_rec, off_pred_prob, off_beta, off_beta_hat, off_qdelta, off_actions, off_expslot, off_path, off_vskey,
-        off_vsval;
+        off_vsval, off_depth;
 };
 
 // device error codes stored in TreeHdr::err / the handle's global error word

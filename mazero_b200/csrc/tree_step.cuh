@@ -1,27 +1,84 @@
 // tree_step.cuh -- the per-tree step functions of the sampled-MCTS tree engine (one warp = one tree), shared by the
 // stand-alone tree kernels (tree_kernels.cuh) and the persistent whole-search kernel (search_persist.cuh).
+//
+// Cost model that shaped this file (measured, B200, profiles/): a tree step is a chain of dependent instructions and L2 round
+// trips run by ONE warp, and every simulation ends with the slowest tree of its group.  A deep, narrow tree used to cost
+// ~2 k cycles per path level in the selection and ~1.2 k in the backup (57 k cycles per simulation at mean depth 12 against
+// 20 k for a typical tree), so ONE deep tree set the pace of the whole search.  Both are depth-independent now:
+//   * backup: one pass over the tree's value log, every entry read ONCE by one lane and scattered to its path level with
+//     shared-memory atomics (an entry (slot, depth) can only belong to the path node at distance `depth` from the leaf);
+//   * selection: when the last path was long, every EXPANDED node picks its child at once (one lane per node; the RNG word
+//     a node would consume is known from its depth), then the path is a pointer chase through shared memory.
+// Every float operation is the reference's, in the reference's order: results are bit-identical in either form.
 #pragma once
 #include "tree_device.cuh"
 
 namespace maz {
 
-// ---- CTree_batch::cbatch_selection -> CTree::select_path / select_child / ucb_score --------------------
-// (cnode.cpp:616-642, 381-413, 337-379, 297-335)
-// Latency-bound pointer chase: ONE memory round trip per tree level.  While the children of the current
-// node are scored, each child's own header (num_children, child_base, visit, pred_value, hidden index) is
-// already in its lane's registers, so descending is a shuffle.  The next few mt19937 outputs are
-// prefetched at kernel start (one raw draw per select_child call).
+// ---- per-warp shared-memory scratch of a tree step ---------------------------------------------------------------------
+struct LevelAcc {                     // one (node, depth) set of SubTreeValueSet, accumulated over the value log
+    unsigned int cnt, nbig;           // entries in the set / in its big half
+    unsigned long long minb, maxs;    // (f2ord(value) << 32 | log position): min over big, max over small
+};
+struct StepScratch {
+    ExpandScratch ex;                 // expansion staging (tree_device.cuh)
+    LevelAcc *acc;                    // [S + 2] backup accumulators, one per path level
+    uint32_t *chase;                  // [S + 2] wide selection: (chosen child slot << 16) | (child's expansion index + 1, 0 = leaf)
+    uint16_t *pathc;                  // [S + 2] copy of the path in shared memory (backup's entry -> level lookup)
+};
+__host__ __device__ inline size_t tree_scratch_bytes(int N, int A, int K, int S)
+{
+    const size_t lv = (size_t)S + 2;
+    size_t b = expand_scratch_bytes(N, A, K) + lv * sizeof(LevelAcc) + lv * 4 + ((lv * 2 + 15) & ~(size_t)15);
+    return (b + 15) & ~(size_t)15;
+}
+__device__ __forceinline__ StepScratch carve_step_scratch(char *p, int N, int A, int K, int S)
+{
+    StepScratch s;
+    s.ex = carve_scratch(p, N, A);
+    p += expand_scratch_bytes(N, A, K);           // (multiple of 16)
+    s.acc = reinterpret_cast<LevelAcc *>(p);
+    p += (size_t)(S + 2) * sizeof(LevelAcc);      // 24-byte entries: stays 8-byte aligned
+    s.chase = reinterpret_cast<uint32_t *>(p);
+    p += (size_t)(S + 2) * 4;
+    s.pathc = reinterpret_cast<uint16_t *>(p);
+    return s;
+}
+
+// ---- CTree::ucb_score (cnode.cpp:297-335), one child -------------------------------------------------------------------------
+// n = parent.visit_count - 1 (clamped to the host tables); mixed float / double arithmetic exactly as the reference's toolchain
+// resolves it: the log term and the prior coefficient come from host-built tables.
+__device__ __forceinline__ float ucb_score_device(const TreeLayout &L, const float *__restrict__ logterm, const double *__restrict__ sqrtn,
+                                                  int n, float discount, float pq, float mn, float mx, int mmc, float prior, int cvis,
+                                                  float rew, float ws, float wt)
+{
+    // pb_c = log((n + c_base + 1)/c_base) + c_init   [float <- double]   (host table)
+    // pb_c *= sqrt(n) / (visit + 1)                   [float <- double product]
+    const float pb_c = (L.pbc_dim > 0) ? L.pbc_table[(size_t)n * L.pbc_dim + min(cvis, L.pbc_dim - 1)]
+                                       : (float)__dmul_rn((double)logterm[n], __ddiv_rn(sqrtn[n], (double)(cvis + 1)));
+    const float prior_score = __fmul_rn(pb_c, prior);
+    float v = 0.0f;
+    if (cvis != 0) v = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), pq);
+    if (mmc > 0) {  // CMinMaxStats::normalize (utils.cpp:95-103)
+        const float delta = __fsub_rn(mx, mn);
+        const float den = (L.delta_lb < delta) ? delta : L.delta_lb;
+        v = __fdiv_rn(__fsub_rn(v, mn), den);
+    }
+    if (v < 0.0f) v = 0.0f;
+    if (v > 1.0f) v = 1.0f;
+    return __fadd_rn(prior_score, v);
+}
+
+// ---- CTree_batch::cbatch_selection -> CTree::select_path / select_child (cnode.cpp:616-642, 381-413, 337-379) ----------------
+// Sequential form: latency-bound pointer chase, ONE memory round trip per tree level.  While the children of the current node are
+// scored (one lane per child), each child's own header is already in its lane's registers, so descending is a shuffle.  The
+// next few mt19937 outputs are prefetched at the start (one raw draw per select_child call).
 __device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ logterm,
                                                    const double *__restrict__ sqrtn, int table_len, float discount, int tree,
                                                    int lane, int *__restrict__ idx_x, int *__restrict__ idx_y,
                                                    int *__restrict__ act_out, int *g_err)
 {
     uint16_t *path = f_path(L, tb);
-    const auto nchild = f_nchild(L, tb);
-    const auto cbase = f_cbase(L, tb);
-    const auto visit = f_visit(L, tb);
-    const auto pred_value = f_pred_value(L, tb);
-    const auto hidx = f_hidx(L, tb);
     uint32_t *mt = f_mt(L, tb);
 
     // round trip 0: tree header, root header, prefetched random words
@@ -62,24 +119,7 @@ __device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb
             int n = vc - 1;
             if (n >= table_len) n = table_len - 1;
             float score = 0.0f;
-            if (lane < C) {
-                // pb_c = log((n + c_base + 1)/c_base) + c_init   [float <- double]   (host table)
-                // pb_c *= sqrt(n) / (visit + 1)                   [float <- double product]
-                const float pb_c = (L.pbc_dim > 0)
-                                       ? L.pbc_table[(size_t)n * L.pbc_dim + min(cvis, L.pbc_dim - 1)]
-                                       : (float)__dmul_rn((double)logterm[n], __ddiv_rn(sqrtn[n], (double)(cvis + 1)));
-                const float prior_score = __fmul_rn(pb_c, prior);
-                float v = 0.0f;
-                if (cvis != 0) v = __fsub_rn(__fadd_rn(rew, __fmul_rn(discount, __fdiv_rn(ws, wt))), pq);
-                if (mmc > 0) {  // CMinMaxStats::normalize (utils.cpp:95-103)
-                    const float delta = __fsub_rn(mx, mn);
-                    const float den = (L.delta_lb < delta) ? delta : L.delta_lb;
-                    v = __fdiv_rn(__fsub_rn(v, mn), den);
-                }
-                if (v < 0.0f) v = 0.0f;
-                if (v > 1.0f) v = 1.0f;
-                score = __fadd_rn(prior_score, v);
-            }
+            if (lane < C) score = ucb_score_device(L, logterm, sqrtn, n, discount, pq, mn, mx, mmc, prior, cvis, rew, ws, wt);
             // sequential epsilon-tie list of cnode.cpp:351-370, evaluated in parallel:
             // list = {first index of the maximum} U {later indices with score >= max - 1e-6f}
             const bool valid = (lane < C) && (score > -1000000.0f);
@@ -143,67 +183,199 @@ __device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb
     for (int j = lane; j < L.N; j += 32) act_out[(size_t)tree * L.N + j] = act[j];
 }
 
+// Wide form: one lane per EXPANDED node.  The child a node would pick depends only on that node's children, the tree's min-max
+// bounds and the raw RNG word its select_child call consumes -- and that word's index is the node's depth (the path holds
+// exactly one node per depth, each consuming one word, except a root still in its forced round-robin: cnode.cpp:398-399,
+// 373-377).  So all choices are made at once (children scored sequentially inside the lane: literally the reference's loop,
+// cnode.cpp:351-370), and the path is then a pointer chase through a shared-memory table.  Returns false, having changed
+// nothing, when the words needed straddle the end of the generator's block (the sequential form regenerates it on the way).
+__device__ __forceinline__ bool select_path_wide(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ logterm,
+                                                 const double *__restrict__ sqrtn, int table_len, float discount, int tree, int lane,
+                                                 const StepScratch &scr, int *__restrict__ idx_x, int *__restrict__ idx_y,
+                                                 int *__restrict__ act_out, int *g_err)
+{
+    const int n_exp = h->n_expanded, mt_pos = h->mt_pos;
+    if (mt_pos + n_exp > kMtN) return false;                 // (a path visits at most n_exp expanded nodes)
+    const float mn = h->mm_min, mx = h->mm_max;
+    const int mmc = h->mm_cnt;
+    const uint32_t *mt = f_mt(L, tb);
+    const uint16_t *expslot = f_expslot(L, tb);
+    const uint16_t *depth = f_depth(L, tb);
+    const RecRegs root = rec_load(L, tb, 0);
+    const int forced = (rec_visit(root) <= rec_nchild(root)) ? 1 : 0;
+#pragma unroll 1
+    for (int e0 = 0; e0 < n_exp; e0 += 32) {
+        const int e = e0 + lane;
+        if (e < n_exp) {
+            const int slot = expslot[e], dep = depth[e];
+            const RecRegs nr = rec_load(L, tb, slot);
+            const int C = rec_nchild(nr), base = rec_cbase(nr), vc = rec_visit(nr);
+            const float pq = rec_pred_value(nr);
+            int ci;
+            if (e == 0 && forced) {
+                ci = vc - 1;
+            } else {
+                const uint32_t word = mt[mt_pos + dep - forced];
+                int n = vc - 1;
+                if (n >= table_len) n = table_len - 1;
+                float max_score = -1000000.0f;               // FLOAT_MIN (utils.h:11-12)
+                unsigned listmask = 0;
+#pragma unroll 2
+                for (int c = 0; c < C; ++c) {
+                    const RecRegs r = rec_load(L, tb, base + c);
+                    const float s = ucb_score_device(L, logterm, sqrtn, n, discount, pq, mn, mx, mmc, rec_prior(r), rec_visit(r),
+                                                     rec_reward(r), rec_wsum(r), rec_wtot(r));
+                    if (max_score < s) {
+                        max_score = s;
+                        listmask = 1u << c;
+                    } else if (s >= __fsub_rn(max_score, 0.000001f)) {
+                        listmask |= 1u << c;
+                    }
+                }
+                const int nl = __popc(listmask);
+                ci = 0;
+                if (nl > 0) {
+                    uint32_t mrem = listmask;
+                    for (uint32_t skip = mt_temper(word) % (uint32_t)nl; skip > 0; --skip) mrem &= mrem - 1;
+                    ci = __ffs(mrem) - 1;
+                }
+            }
+            const int cs = base + ci;
+            const RecRegs cr = rec_load(L, tb, cs);          // (just scored: L1)
+            const int ceid = (rec_nchild(cr) > 0) ? rec_eid(cr) + 1 : 0;      // expanded() = num_children > 0
+            scr.chase[e] = ((uint32_t)cs << 16) | (uint32_t)ceid;
+        }
+    }
+    __syncwarp();
+    // the path: root -> chosen child -> ... until an unexpanded node
+    uint16_t *path = f_path(L, tb);
+    int e = 0, len = 0, node = 0, parent = 0, err = 0;
+    if (lane == 0) path[0] = 0;
+    while (true) {
+        const uint32_t w = scr.chase[e];                     // (same address in every lane: broadcast)
+        parent = node;
+        node = (int)(w >> 16);
+        ++len;
+        if (len > L.S + 1) {
+            err = kErrPathOverflow;
+            break;
+        }
+        if (lane == 0) path[len] = (uint16_t)node;
+        const int ne = (int)(w & 0xffffu);
+        if (ne == 0) break;
+        e = ne - 1;
+    }
+    if (lane == 0) {
+        h->path_len = len;
+        h->mt_pos = mt_pos + len - forced;                   // one word per select_child call
+        h->sum_path_len += len;
+        idx_x[tree] = f_hidx(L, tb)[parent];                 // hidden_state_index_x of the leaf's parent
+        idx_y[tree] = tree;
+        if (err) {
+            h->err = err;
+            *g_err = err;
+        }
+    }
+    const uint8_t *act = f_actions(L, tb) + (size_t)node * L.N;
+    for (int j = lane; j < L.N; j += 32) act_out[(size_t)tree * L.N + j] = act[j];
+    return true;
+}
+
+// the selection of the next simulation: wide when the last path was long (scr may be NULL: sequential only)
+__device__ __forceinline__ void select_next_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ logterm,
+                                                   const double *__restrict__ sqrtn, int table_len, float discount, int tree,
+                                                   int lane, const StepScratch *scr, int *__restrict__ idx_x, int *__restrict__ idx_y,
+                                                   int *__restrict__ act_out, int *g_err)
+{
+    if (scr != nullptr && h->path_len >= L.wide_min_len &&
+        select_path_wide(L, tb, h, logterm, sqrtn, table_len, discount, tree, lane, *scr, idx_x, idx_y, act_out, g_err))
+        return;
+    select_path_device(L, tb, h, logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
+}
+
 // ---- CTree::back_propagate (cnode.cpp:415-450), shared by every kernel --------------------------------------------------
 // The reference walks the path leaf -> root; per node: visit++, subtree_info.update(G, depth), q-delta entry, G = r + gamma G.
 // Only the scalar recurrence of G is sequential.  The value-set update of a path node touches ONLY its own (slot, depth) set --
 // entries appended / flags flipped for one node never match another node's tag, and the append positions are known up front
-// (log_len0 + distance from the leaf) -- so all levels are processed IN PARALLEL: a group of 32 / pow2(levels) lanes per level
-// scans a snapshot of the tree's value log for that level's set, combines, and its leader applies the reference's exact fp32
-// update (vs_decide).  Cost: one pass over the log, whatever the depth (the sequential form cost ~1.2 k cycles per level and
-// made the deepest tree of a batch the pace-setter of every simulation).
-constexpr int kLogCache = 256;    // log entries staged in shared memory per tree; a longer log's tail is read from global memory
-__host__ __device__ inline size_t backup_scratch_bytes() { return (size_t)kLogCache * 8; }
+// (log_len0 + distance from the leaf) -- so all levels are updated in parallel, one lane per level, from per-level
+// accumulators filled by ONE pass over the value log.
+constexpr int kLogRegs = 8;   // 8 x 32 log entries requested up front (before the expansion); longer logs: tail read in the pass
 
-// per-warp shared-memory scratch of a tree step: the expansion's staging + the log cache
-__host__ __device__ inline size_t tree_scratch_bytes(int N, int A, int K) { return expand_scratch_bytes(N, A, K) + backup_scratch_bytes(); }
-
-struct LogCache {
-    uint32_t *k;        // [kLogCache] keys   (shared memory)
-    float *v;           // [kLogCache] values
+struct LogRegs {
+    uint32_t k[kLogRegs];
+    float v[kLogRegs];
 };
-__device__ __forceinline__ LogCache carve_log_cache(char *p)
-{
-    return LogCache{reinterpret_cast<uint32_t *>(p), reinterpret_cast<float *>(p + 4 * kLogCache)};
-}
-// stage entries [from, min(to, kLogCache)) of the tree's value log
-__device__ __forceinline__ void log_cache_fill(const TreeLayout &L, char *tb, const LogCache &lc, int from, int to, int lane)
+__device__ __forceinline__ void log_prefetch(const TreeLayout &L, char *tb, int log_len0, int lane, LogRegs &lr)
 {
     const uint32_t *vk = f_vskey(L, tb);
     const float *vv = f_vsval(L, tb);
-    const int n = min(to, kLogCache);
-    for (int e = from + lane; e < n; e += 32) {
-        lc.k[e] = vk[e];
-        lc.v[e] = vv[e];
+#pragma unroll
+    for (int c = 0; c < kLogRegs; ++c) {
+        const int e = c * 32 + lane;
+        lr.k[c] = (e < log_len0) ? vk[e] : 0xffffffffu;   // depth 0x7fff never matches a path level
+        lr.v[c] = (e < log_len0) ? vv[e] : 0.0f;
+    }
+}
+// one log entry -> the accumulators of the path level it belongs to (if any)
+__device__ __forceinline__ void backup_scatter_entry(const StepScratch &scr, int len, uint32_t k, float v, int e)
+{
+    const int i = len - (int)((k >> 1) & 0x7fffu);        // the path node at distance `depth` from the leaf
+    if (i >= 0 && scr.pathc[i] == (uint16_t)(k >> 16)) {
+        LevelAcc *a = scr.acc + i;
+        const unsigned long long oe = ((unsigned long long)f2ord(v) << 32) | (unsigned int)e;
+        atomicAdd(&a->cnt, 1u);
+        if (k & 1u) {
+            atomicAdd(&a->nbig, 1u);
+            atomicMin(&a->minb, oe);
+        } else {
+            atomicMax(&a->maxs, oe);
+        }
     }
 }
 
-// leaf -> root.  `len` = SearchResult::search_len, path[0..len] the path's node slots; `leaf_eid` = expansion order the leaf gets
-// in this simulation; reward_in / value = this simulation's network outputs; the log cache holds entries [0, min(log_len0,
-// kLogCache)) as they were BEFORE this backup.  Writes visit / wsum / wtot of every path node (the leaf's included), the
-// q-delta entries and the log appends (global memory, and the cache when `keep_cache`).  Warp-uniform log_len / err.
-__device__ __forceinline__ void backup_parallel(const TreeLayout &L, char *tb, const float *__restrict__ lam_pow, const LogCache &lc,
-                                                const uint16_t *__restrict__ path, int len, int log_len0, int leaf_eid,
-                                                float reward_in, float value, float discount, int lane, int &log_len, int &err,
-                                                bool keep_cache = false)
+// leaf -> root.  `len` = SearchResult::search_len, path[0..len] the path's node slots (global memory); `leaf_eid` = expansion
+// order the leaf gets in this simulation; reward_in / value = this simulation's network outputs; `lr` = the first 256 entries of
+// the log as they were BEFORE this backup.  Writes visit / wsum / wtot of every path node (the leaf's included), the q-delta
+// entries and the log appends.  Warp-uniform log_len / err.
+__device__ __forceinline__ void backup_parallel(const TreeLayout &L, char *tb, const float *__restrict__ lam_pow, const StepScratch &scr,
+                                                const LogRegs &lr, const uint16_t *__restrict__ path, int len, int log_len0, int leaf_eid,
+                                                float reward_in, float value, float discount, int lane, int &log_len, int &err)
 {
     uint32_t *vk = f_vskey(L, tb);
     float *vv = f_vsval(L, tb);
     float *qd = f_qdelta(L, tb);                      // q-delta of the e-th expanded node (the CMinMaxStats entries)
-    const int ncache = min(log_len0, kLogCache);
+    // ---- pass over the log: every entry is looked at once -----------------------------------------------------------------
+    for (int i = lane; i <= len; i += 32) {
+        scr.pathc[i] = path[i];
+        scr.acc[i].cnt = 0u; scr.acc[i].nbig = 0u; scr.acc[i].minb = ~0ull; scr.acc[i].maxs = 0ull;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < kLogRegs; ++c) backup_scatter_entry(scr, len, lr.k[c], lr.v[c], c * 32 + lane);
+    for (int e0 = kLogRegs * 32; e0 < log_len0; e0 += 128) {         // tail: four independent loads per lane in flight
+        uint32_t k[4];
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + 32 * u + lane;
+            k[u] = (e < log_len0) ? vk[e] : 0xffffffffu;
+            v[u] = (e < log_len0) ? vv[e] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) backup_scatter_entry(scr, len, k[u], v[u], e0 + 32 * u + lane);
+    }
+    __syncwarp();
+    // ---- one lane per path level, chunks of 32 levels, leaf first -----------------------------------------------------------
     float G = value;
 #pragma unroll 1
-    for (int base = len; base >= 0; base -= 32) {     // chunks of up to 32 path levels, leaf first
+    for (int base = len; base >= 0; base -= 32) {
         const int nlev = min(32, base + 1);
-        int gl = 1;
-        while (gl < nlev) gl <<= 1;                   // levels rounded up to a power of two
-        const int gs = 32 / gl;                       // lanes per level
-        const int lev = lane / gs, sub = lane - lev * gs;
-        const bool active = lev < nlev;
-        const int i = base - lev;                     // path index of my level
+        const bool active = lane < nlev;
+        const int i = base - lane;                    // path index of my level
         int slot = 0, vis = 0, nh = 0;
         float rew = 0.f, ws = 0.f, wt = 0.f, ppv = 0.f, lp = 0.f;
         if (active) {
-            slot = path[i];
+            slot = scr.pathc[i];
             lp = lam_pow[len - i];
             if (i == len) {                           // the freshly expanded leaf
                 rew = reward_in; nh = leaf_eid;
@@ -211,48 +383,31 @@ __device__ __forceinline__ void backup_parallel(const TreeLayout &L, char *tb, c
                 const RecRegs q = rec_load(L, tb, slot);
                 rew = rec_reward(q); ws = rec_wsum(q); wt = rec_wtot(q); vis = rec_visit(q); nh = rec_eid(q);
             }
-            if (i > 0) ppv = f_pred_value(L, tb)[path[i - 1]];     // parent's pred_value
+            if (i > 0) ppv = f_pred_value(L, tb)[scr.pathc[i - 1]];     // parent's pred_value
         }
         // G of every level: the reference's sequential recurrence, in its order
         float myG = 0.f;
         for (int l = 0; l < nlev; ++l) {
-            const float r_l = __shfl_sync(MAZ_FULL, rew, l * gs);
-            if (lev == l) myG = G;
+            const float r_l = __shfl_sync(MAZ_FULL, rew, l);
+            if (lane == l) myG = G;
             G = __fadd_rn(r_l, __fmul_rn(discount, G));
         }
         // (the reference removes the node's old q-delta from the min-max multiset first; here the entry simply lives in
         //  qd[expansion order] and is overwritten below)
-        const uint32_t tag = vs_tag(slot, len - i);
-        VsScan r;
-        vs_scan_init(r);
-        if (active) {
-            for (int e = sub; e < ncache; e += gs) vs_scan_entry(r, tag, lc.k[e], lc.v[e], e);
-            for (int e = kLogCache + sub; e < log_len0; e += gs) vs_scan_entry(r, tag, vk[e], vv[e], e);
-        }
-        for (int o = 1; o < gs; o <<= 1) {            // combine the group's partial scans
-            const int ocnt = __shfl_xor_sync(MAZ_FULL, r.cnt, o), onbig = __shfl_xor_sync(MAZ_FULL, r.nbig, o);
-            const uint32_t omin = __shfl_xor_sync(MAZ_FULL, r.minbig, o), omax = __shfl_xor_sync(MAZ_FULL, r.maxsmall, o);
-            const int ominpos = __shfl_xor_sync(MAZ_FULL, r.minpos, o), omaxpos = __shfl_xor_sync(MAZ_FULL, r.maxpos, o);
-            r.cnt += ocnt; r.nbig += onbig;
-            if (ominpos >= 0 && (r.minpos < 0 || omin < r.minbig)) { r.minbig = omin; r.minpos = ominpos; }
-            if (omaxpos >= 0 && (r.maxpos < 0 || omax > r.maxsmall)) { r.maxsmall = omax; r.maxpos = omaxpos; }
-        }
         int myerr = 0;
-        if (active && sub == 0) {
-            const VsDecision d = vs_decide(L, r.cnt, r.nbig, r.minbig, r.minpos, r.maxsmall, r.maxpos, tag, lp, myG, ws, wt);
+        if (active) {
+            const LevelAcc a = scr.acc[i];
+            const uint32_t tag = vs_tag(slot, len - i);
+            const VsDecision d = vs_decide(L, (int)a.cnt, (int)a.nbig, (uint32_t)(a.minb >> 32), (int)(uint32_t)a.minb,
+                                           (uint32_t)(a.maxs >> 32), (int)(uint32_t)a.maxs, tag, lp, myG, ws, wt);
             myerr = d.err;
-            const int pos = log_len + lev;            // the reference appends leaf first
+            const int pos = log_len + lane;           // the reference appends leaf first
             if (pos >= L.L) {
                 myerr = kErrLogOverflow;
             } else {
-                const uint32_t key = tag | (d.append_big ? 1u : 0u);
                 if (d.flip_pos >= 0) vk[d.flip_pos] = d.flip_key;
-                vk[pos] = key;
+                vk[pos] = tag | (d.append_big ? 1u : 0u);
                 vv[pos] = myG;
-                if (keep_cache) {
-                    if (d.flip_pos >= 0 && d.flip_pos < kLogCache) lc.k[d.flip_pos] = d.flip_key;
-                    if (pos < kLogCache) { lc.k[pos] = key; lc.v[pos] = myG; }
-                }
             }
             f_visit(L, tb)[slot] = vis + 1;
             f_wsum(L, tb)[slot] = ws;
@@ -287,7 +442,7 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
                                                      int hidx, float discount, int K, const float *__restrict__ reward_ptr,
                                                      const float *__restrict__ value_ptr,
                                                      const float *__restrict__ probs, const float *__restrict__ beta,
-                                                     const ExpandScratch &sc, const LogCache &lc, int lane, int *g_err, int tree = -1)
+                                                     const StepScratch &scr, int lane, int *g_err, int tree = -1)
 {
     MAZ_TS(L, tree, lane, 0);
     griddep_launch();   // PDL: the next kernel (inference of the next simulation) may start its prologue now
@@ -296,12 +451,13 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
     const int log_len0 = log_len;
     const int leaf_eid = n_expanded;                  // expansion order the leaf is about to get
     MAZ_TS(L, tree, lane, 1);
-    log_cache_fill(L, tb, lc, 0, log_len0, lane);
+    LogRegs lr;
+    log_prefetch(L, tb, log_len0, lane, lr);
     const int n_draw = (L.A >= 2) ? 2 * K * L.N : 0;
     const bool draws_pre = n_draw > 0 && n_draw <= kMtChunk && mt_pos + n_draw <= kMtN;
     if (draws_pre) {
         const uint32_t *mt = f_mt(L, tb);
-        for (int t = lane; t < n_draw; t += 32) sc.draws[t] = mt_temper(mt[mt_pos + t]);
+        for (int t = lane; t < n_draw; t += 32) scr.ex.draws[t] = mt_temper(mt[mt_pos + t]);
         mt_pos += n_draw;
     }
     const uint16_t *path = f_path(L, tb);
@@ -311,10 +467,10 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
     // complete); the network outputs of THIS simulation are produced by the kernel we may be overlapping with.
     griddep_wait();
     const float reward_in = __ldcg(reward_ptr), value = __ldcg(value_ptr);   // L2 loads, see expand_node
-    expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, reward_in, value, probs, beta, K, 0.0f, nullptr, sc,
-                lane, draws_pre, tree);
+    expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, reward_in, value, probs, beta, K, 0.0f, nullptr, scr.ex,
+                lane, draws_pre, tree, /*init_stats=*/true, /*depth=*/len);
     MAZ_TS(L, tree, lane, 3);
-    backup_parallel(L, tb, lam_pow, lc, path, len, log_len0, leaf_eid, reward_in, value, discount, lane, log_len, err);
+    backup_parallel(L, tb, lam_pow, scr, lr, path, len, log_len0, leaf_eid, reward_in, value, discount, lane, log_len, err);
     MAZ_TS(L, tree, lane, 4);
     float mn, mx;
     minmax_reduce(L, tb, n_expanded, lane, mn, mx);
