@@ -74,11 +74,10 @@ constexpr uint32_t OFF_W = ((OFF_ROW + TM * 16 + 127) / 128) * 128;   // weight 
 constexpr uint32_t OFF_P = OFF_W + NSLOT * SLOT_BYTES;           // fp32 parameters (d.vec)
 // fp32 scratch inside the Q region (heads only), in floats
 constexpr int G_R = 0, G_V = TM * LDG;                           // graph sums of the reward / value GNN   [TM][LDG]
-constexpr int Y_R = 0, Y_V = TM * GH;                            // normalised layer-2 features (over G)   [TM][GH]
+constexpr int Y_R = 0, Y_V = TM * GH;                            // layer-2 features (fp32, in the X + T tiles) [TM][GH]
 constexpr int PL0 = 2 * TM * LDG;                                // policy logits                          [TM][48]
 static_assert((PL0 + TM * 48) * 4 <= TM * LDQ, "heads scratch must fit in the q|k|v region");
-static_assert(2 * TM * GH * 4 <= 2 * TM * LDA, "pooled features must fit in the X + T tiles");
-static_assert(TM * 2 * 12 * 4 <= 3 * TM * NQ * 8, "head logits must fit in the statistics region");
+static_assert(2 * TM * GH * 4 <= 2 * TM * LDA, "layer-2 features must fit in the X + T tiles");
 
 using Desc = ::maz_infer_desc;
 
@@ -90,16 +89,20 @@ __device__ __forceinline__ int tile_rpt(const Desc &d) { return d.roots_per_tile
 // The per-simulation pointers: constants of the descriptor for the one-step kernel, advanced per simulation by the
 // persistent whole-search kernel (search_persist.cuh).
 struct SimIo {
+    // the exchange arrays between the tree step and the network: indexed by (root - root0).  Global memory with root0 = 0 for the
+    // one-step kernel; the persistent kernel keeps its CTA's slice of them in SHARED memory (root0 = the CTA's first root).
     const int *idx_x;      // (B,) pool index of the parent
     const int *actions;    // (B,N) joint action, or (B,1) tree action when the joint action is assembled here
-    float *next_hidden;    // (B, N*H)
     float *reward, *value, *probs, *beta;
+    int root0;
+    // global memory, indexed by the root
+    float *next_hidden;    // (B, N*H)
     int *greedy;           // (B,N) or NULL
     float *logits_out;     // (B,N,A) or NULL
 };
 __device__ __forceinline__ SimIo io_from_desc(const Desc &d)
 {
-    return SimIo{d.idx_x, d.actions, d.next_hidden, d.reward, d.value, d.probs, d.beta, d.greedy, d.logits_out};
+    return SimIo{d.idx_x, d.actions, d.reward, d.value, d.probs, d.beta, 0, d.next_hidden, d.greedy, d.logits_out};
 }
 
 __host__ __device__ inline size_t smem_bytes(int vec_floats) { return (size_t)OFF_P + (size_t)vec_floats * 4 + 128; }
@@ -207,7 +210,22 @@ __device__ __forceinline__ void gemm_rt(float (&acc)[NT][4], const Thr &th, uint
     }
 }
 
-// ---- weight ring (consumer side) ---------------------------------------------------------------------------------
+// ---- weight ring ---------------------------------------------------------------------------------------------------------
+// one chunk = several bulk copies on the same mbarrier (16 weight rows each)
+__device__ __forceinline__ void issue_chunk(const Desc &d, int k, int slot, uint64_t *bar_full)
+{
+    HSM_DECL;
+    const uint32_t nbytes = (d.dbg_flags & 4) ? 16u : d.chunk_bytes[k];   // profiling: tiny copies
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(d.wpk) + d.chunk_off[k];
+    uint8_t *dst = hsm + OFF_W + (size_t)slot * SLOT_BYTES;
+    mbar_expect_tx(&bar_full[slot], nbytes);
+    for (uint32_t o = 0; o < nbytes; o += PIECE) {
+        const uint32_t n = (nbytes - o < PIECE) ? (nbytes - o) : PIECE;
+        bulk_g2s(dst + o, src + o, n, &bar_full[slot]);
+    }
+}
+
+// Consumer side (a dedicated producer warp keeps the ring full: produce_weights).
 struct Ring {
     uint64_t *full, *empty;
     int c;
@@ -635,7 +653,7 @@ static __device__ __noinline__ void stage_dynamics(const Desc &d, Ring &ring, co
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
         const RowInfo &ri = hf ? rb : ra;
-        const int ix = (ri.valid && io.idx_x) ? __ldcg(io.idx_x + ri.root) : 0;
+        const int ix = (ri.valid && io.idx_x) ? io.idx_x[ri.root - io.root0] : 0;   // (plain load: global or shared)
         const float *hp = d.pool + ((size_t)ix * d.B + (ri.valid ? ri.root : 0)) * (size_t)(d.N * H) + (size_t)ri.agent * H;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
@@ -786,12 +804,9 @@ static __device__ __noinline__ void stage_heads1(const Desc &d, Ring &ring)
     cta_sync();
 }
 
-// softmax . support -> inv_h (core/config.py:430-442, 463-499); lg: shared address of 11 logits
-__device__ __forceinline__ float support_to_scalar(uint32_t lg)
+// softmax . support -> inv_h (core/config.py:430-442, 463-499) of 11 logits
+__device__ __forceinline__ float support_to_scalar(const float (&v)[SUP])
 {
-    float v[SUP];
-#pragma unroll
-    for (int k = 0; k < SUP; ++k) v[k] = lds1v(lg + 4u * k);
     float m = v[0];
 #pragma unroll
     for (int k = 1; k < SUP; ++k) m = fmaxf(m, v[k]);
@@ -814,16 +829,15 @@ __device__ __forceinline__ float support_to_scalar(uint32_t lg)
 
 // heads, second layers + outputs, ONE stage: reward / value GNN layer 2 -> mean over agents -> 64->11 head -> scalar;
 // fc_policy.3 -> softmax / beta / greedy (mcts_sampled.py:158-161).
-static __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring, const SimIo io)
+static __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring, const SimIo io, long long *hs_clk)
 {
     const Thr th;
     const uint32_t sb = sbase();
     const int n0 = CW * th.nq, ldg = (GH + PAD) * 2;
     const int N = d.N, A = d.A, tid = threadIdx.x;
     int hs_n = 40;
-    const bool hs_on = d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0;
 #define HS() \
-    if (hs_on && hs_n < 64) d.dbg_clock[hs_n++] = clock64();
+    if (hs_clk && hs_n < 64) hs_clk[hs_n++] = clock64();
     HS();
     float aR[NT][4], aV[NT][4], aP[2][4];
     zero<NT>(aR); zero<NT>(aV); zero<2>(aP);
@@ -860,6 +874,16 @@ static __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring, cons
     float yR[GT][4], yV[GT][4];
     gnn_phase_b(aR, th, G + 4u * G_R, pr, stat, N, r0A, r0B, yR);
     gnn_phase_b(aV, th, G + 4u * G_V, pvv, stat + STAT_SET, N, r0A, r0B, yV);
+    // the raw (post-ReLU) layer-2 features, fp32 -> Y in the X + T tiles (free since the GEMMs above)
+    const uint32_t YB = sb + OFF_X;
+#pragma unroll
+    for (int tl = 0; tl < GT; ++tl) {
+        const int f = FW * th.nq + 8 * tl + 2 * th.t;
+        sts2f(YB + 4u * (Y_R + th.rA * GH + f), yR[tl][0], yR[tl][1]);
+        sts2f(YB + 4u * (Y_R + th.rB * GH + f), yR[tl][2], yR[tl][3]);
+        sts2f(YB + 4u * (Y_V + th.rA * GH + f), yV[tl][0], yV[tl][1]);
+        sts2f(YB + 4u * (Y_V + th.rB * GH + f), yV[tl][2], yV[tl][3]);
+    }
     HS();
     if (tid < TM * 8) {   // policy outputs: 8 threads per row (softmax, beta, greedy); warp-uniform condition
         const int r = tid >> 3, sub = tid & 7;
@@ -900,7 +924,7 @@ static __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring, cons
                 if (io.logits_out) io.logits_out[((size_t)ri.root * N + ri.agent) * A + a] = v;
                 if (ta >= 0) {
                     const float e = __expf(v - m);
-                    const size_t o = ((size_t)ri.root * d.Nt + ta) * A + a;
+                    const size_t o = ((size_t)(ri.root - io.root0) * d.Nt + ta) * A + a;
                     io.probs[o] = e * invs;
                     io.beta[o] = (unit_tau ? e : __powf(e, d.inv_tau)) * invb;
                 }
@@ -910,70 +934,70 @@ static __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring, cons
     HS();
     cta_sync();
     HS();
-    // phase C: normalised features (fp32) -> Y (over G, which nobody reads any more)
-    gnn_phase_c(th, stat, yR);
-    gnn_phase_c(th, stat + STAT_SET, yV);
-#pragma unroll
-    for (int tl = 0; tl < GT; ++tl) {
-        const int f = FW * th.nq + 8 * tl + 2 * th.t;
-        sts2f(G + 4u * (Y_R + th.rA * GH + f), yR[tl][0], yR[tl][1]);
-        sts2f(G + 4u * (Y_R + th.rB * GH + f), yR[tl][2], yR[tl][3]);
-        sts2f(G + 4u * (Y_V + th.rA * GH + f), yV[tl][0], yV[tl][1]);
-        sts2f(G + 4u * (Y_V + th.rB * GH + f), yV[tl][2], yV[tl][3]);
-    }
-    cta_sync();
-    HS();
-    // phase D: mean over the agents of a root -> pooled[kind][root][f] (fp32) in the X + T tiles (free since the GEMMs above)
+    // phase D: per root and head, the mean over its agents of LayerNorm(y) (no affine: model.py:157,163) -> pooled (fp32) at the
+    // start of the G region (nobody reads G any more).  The row statistics are applied on the fly: no separate normalisation
+    // phase, no barrier for it.
     const int rpt = tile_rpt(d);
-    const uint32_t POOL = sb + OFF_X;
+    const uint32_t POOL = G;
     const float invn = 1.f / (float)N;
     for (int i = tid; i < 2 * rpt * (GH / 2); i += NCONS) {
         const int f2 = i & (GH / 2 - 1), rest = i >> 5, kind = rest >= rpt ? 1 : 0, rl = rest - kind * rpt;
-        const uint32_t src = G + 4u * ((kind ? Y_V : Y_R) + (rl * N) * GH + 2 * f2);
+        const uint32_t src = YB + 4u * ((kind ? Y_V : Y_R) + (rl * N) * GH + 2 * f2), st = stat + (kind ? STAT_SET : 0u);
         float2 s = make_float2(0.f, 0.f);
         int j = 0;
 #pragma unroll 1
         for (; j + 3 <= N; j += 3) {
+            float m0, r0, m1, r1, m2, r2;
+            stats_read(st, rl * N + j, 1.f / GH, m0, r0);
+            stats_read(st, rl * N + j + 1, 1.f / GH, m1, r1);
+            stats_read(st, rl * N + j + 2, 1.f / GH, m2, r2);
             const float2 v0 = lds2f(src + 4u * (j * GH)), v1 = lds2f(src + 4u * ((j + 1) * GH)), v2 = lds2f(src + 4u * ((j + 2) * GH));
-            s.x += v0.x + v1.x + v2.x; s.y += v0.y + v1.y + v2.y;
+            s.x += (v0.x - m0) * r0 + (v1.x - m1) * r1 + (v2.x - m2) * r2;
+            s.y += (v0.y - m0) * r0 + (v1.y - m1) * r1 + (v2.y - m2) * r2;
         }
 #pragma unroll 1
         for (; j < N; ++j) {
+            float m0, r0;
+            stats_read(st, rl * N + j, 1.f / GH, m0, r0);
             const float2 v = lds2f(src + 4u * (j * GH));
-            s.x += v.x; s.y += v.y;
+            s.x += (v.x - m0) * r0; s.y += (v.y - m0) * r0;
         }
         sts2f(POOL + 4u * ((kind * rpt + rl) * GH + 2 * f2), s.x * invn, s.y * invn);
     }
     cta_sync();
     HS();
-    // phase E: logits of the 64 -> 11 heads, thread = (root, kind, k), weights from the padded copy (conflict-free float4 rows)
-    const uint32_t LG = sb + OFF_STAT;                             // [rpt][2][12] floats (the statistics are consumed)
-    for (int i = tid; i < rpt * 2 * SUP; i += NCONS) {
-        const int k = i % SUP, rest = i / SUP, kind = rest & 1, rl = rest >> 1;
-        const uint32_t pv = POOL + 4u * ((kind * rpt + rl) * GH), vw = sb + OFF_VP + 4u * ((kind * SUP + k) * LDV);
-        float s0 = 0.f, s1 = 0.f;
+    // phase E: a half-warp per (root, head): lane k < 11 computes logit k of the 64 -> 11 head (weights from the padded copy:
+    // conflict-free float4 rows), the 11 logits meet in the half-warp's first lane by shuffles, which applies
+    // softmax . support -> inv_h and stores the scalar.  No barrier, no shared-memory round trip.
+    {
+        const int hw = tid >> 4, l16 = tid & 15, lane = tid & 31;
+        for (int pair = hw; pair < rpt * 2; pair += NCONS / 16) {      // (both half-warps of a warp run the same number of rounds)
+            const int rl = pair >> 1, kind = pair & 1;
+            float logit = 0.f;
+            if (l16 < SUP) {
+                const uint32_t pv = POOL + 4u * ((kind * rpt + rl) * GH), vw = sb + OFF_VP + 4u * ((kind * SUP + l16) * LDV);
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int f = 0; f < GH; f += 32) {          // 8 volatile loads in flight, then the math
-            float4 a[8], wv[8];
+                for (int f = 0; f < GH; f += 32) {          // 8 volatile loads in flight, then the math
+                    float4 a[8], wv[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) a[q] = lds4v(pv + 4u * (f + 4 * q));
+                    for (int q = 0; q < 8; ++q) a[q] = lds4v(pv + 4u * (f + 4 * q));
 #pragma unroll
-            for (int q = 0; q < 8; ++q) wv[q] = lds4(vw + 4u * (f + 4 * q));
+                    for (int q = 0; q < 8; ++q) wv[q] = lds4(vw + 4u * (f + 4 * q));
 #pragma unroll
-            for (int q = 0; q < 8; q += 2) {
-                s0 += a[q].x * wv[q].x + a[q].y * wv[q].y + a[q].z * wv[q].z + a[q].w * wv[q].w;
-                s1 += a[q + 1].x * wv[q + 1].x + a[q + 1].y * wv[q + 1].y + a[q + 1].z * wv[q + 1].z + a[q + 1].w * wv[q + 1].w;
+                    for (int q = 0; q < 8; q += 2) {
+                        s0 += a[q].x * wv[q].x + a[q].y * wv[q].y + a[q].z * wv[q].z + a[q].w * wv[q].w;
+                        s1 += a[q + 1].x * wv[q + 1].x + a[q + 1].y * wv[q + 1].y + a[q + 1].z * wv[q + 1].z + a[q + 1].w * wv[q + 1].w;
+                    }
+                }
+                logit = s0 + s1 + lds1(sb + OFF_P + 4u * ((kind ? d.o_vg : d.o_rg) + 256 + SUP * GH + l16));
             }
+            float v[SUP];
+#pragma unroll
+            for (int k = 0; k < SUP; ++k) v[k] = __shfl_sync(0xffffffffu, logit, (lane & 16) + k);
+            const int root = blockIdx.x * rpt + rl;
+            if (l16 == 0 && root < d.B) (kind ? io.value : io.reward)[root - io.root0] = support_to_scalar(v);
         }
-        const float bias = lds1(sb + OFF_P + 4u * ((kind ? d.o_vg : d.o_rg) + 256 + SUP * GH + k));
-        sts1f(LG + 4u * ((rl * 2 + kind) * 12 + k), s0 + s1 + bias);
-    }
-    cta_sync();
-    HS();
-    if (tid < rpt * 2) {
-        const int rl = tid >> 1, kind = tid & 1;
-        const int root = blockIdx.x * rpt + rl;
-        if (root < d.B) (kind ? io.value : io.reward)[root] = support_to_scalar(LG + 4u * ((rl * 2 + kind) * 12));
     }
     HS();
 #undef HS
@@ -1008,15 +1032,7 @@ __device__ __forceinline__ void produce_weights(const Desc &d, uint64_t *bar_ful
     for (int c = 0, k = 0; c < total; ++c, k = (k + 1 == NCHUNK) ? 0 : k + 1) {
         const int s = c % NSLOT;
         if (c >= NSLOT) mbar_wait_backoff(&bar_empty[s], ((c / NSLOT) - 1) & 1);
-        // one chunk = several bulk copies on the same mbarrier (16 weight rows each)
-        const uint32_t nbytes = (d.dbg_flags & 4) ? 16u : d.chunk_bytes[k];   // profiling: tiny copies
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(d.wpk) + d.chunk_off[k];
-        uint8_t *dst = hsm + OFF_W + (size_t)s * SLOT_BYTES;
-        mbar_expect_tx(&bar_full[s], nbytes);
-        for (uint32_t o = 0; o < nbytes; o += PIECE) {
-            const uint32_t n = (nbytes - o < PIECE) ? (nbytes - o) : PIECE;
-            bulk_g2s(dst + o, src + o, n, &bar_full[s]);
-        }
+        issue_chunk(d, k, s, bar_full);
     }
 }
 
@@ -1061,7 +1077,7 @@ __device__ __forceinline__ void infer_stages(const Desc &d, const SimIo io, Ring
     TS();
     stage_heads1(d, ring);
     TS();
-    stage_heads2(d, ring, io);
+    stage_heads2(d, ring, io, clk);
     TS();
 #undef TS
 }

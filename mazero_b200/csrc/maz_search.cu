@@ -147,9 +147,12 @@ int maz_search_create(maz_search **out, const maz_search_config *cfg)
     int rpt = rpt_fit < 8 ? rpt_fit : 8;                            // one warp per tree, 8 compute warps
     const int rpt_env = env_int("MAZ_SEARCH_RPT", 0);
     if (rpt_env > 0 && rpt_env < rpt) rpt = rpt_env;
+    // the persistent kernel's shared memory: the inference map + the trees' hot state and the exchange arrays
+    int optin = 227 * 1024;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     bool persist_ok = cfg->net_kind == MAZ_NET_SMAC && N <= hmma::TM && rpt >= 1 &&
                       (size_t)rpt * tree_scratch_bytes(s->Nt, A, K, S) <= persist::TREE_SCRATCH_BYTES &&
-                      hmma::smem_bytes(s->sm.vec_floats) <= 227 * 1024;
+                      persist::persist_smem_bytes(s->sm.vec_floats, rpt, s->Nt, A, S) + 256 <= (size_t)optin;
     if (strat == MAZ_SEARCH_PERSISTENT && !persist_ok) {
         set_last_error(MAZ_ERR_UNSUPPORTED, "maz_search_create: the persistent kernel does not support this network / shape");
         return fail(MAZ_ERR_UNSUPPORTED);
@@ -193,14 +196,23 @@ int maz_search_create(maz_search **out, const maz_search_config *cfg)
         return fail(MAZ_ERR_CUDA);
     }
     if (s->strategy == MAZ_SEARCH_PERSISTENT) {
-        int optin = 227 * 1024;
-        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
         cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, persist::k_search_persistent);
+        cudaError_t e = cudaFuncGetAttributes(&fa, persist::k_search_persistent<false>);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(persist::k_search_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+            e = cudaFuncSetAttribute(persist::k_search_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(persist::k_search_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) {
             set_last_error(MAZ_ERR_CUDA, std::string("cudaFuncSetAttribute(k_search_persistent): ") + cudaGetErrorString(e));
+            return fail(MAZ_ERR_CUDA);
+        }
+        int nb = 0;
+        const size_t dyn = persist::persist_smem_bytes(s->sm.vec_floats, rpt, s->Nt, A, S);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, persist::k_search_persistent<false>, persist::PERSIST_THREADS, dyn);
+        if (e != cudaSuccess || nb < 1) {
+            set_last_error(MAZ_ERR_CUDA, "k_search_persistent does not fit on an SM: " + std::to_string(fa.numRegs) + " registers x " +
+                                             std::to_string(persist::PERSIST_THREADS) + " threads, " + std::to_string(dyn) + " + " +
+                                             std::to_string(fa.sharedSizeBytes) + " bytes of shared memory (opt-in limit " + std::to_string(optin) + ")");
             return fail(MAZ_ERR_CUDA);
         }
     } else {
@@ -401,7 +413,7 @@ static int graph_for(maz_search *s, const maz_search_call *c, cudaGraphExec_t *o
 
 static int launch_persistent(maz_search *s, const maz_search_call *c, bool record)
 {
-    const int B = s->cfg.B, N = s->cfg.N;
+    const int B = s->cfg.B;
     const bool seq = !s->cfg.joint;
     maz_tree *t = s->tree;
     persist::SearchParams P;
@@ -410,10 +422,8 @@ static int launch_persistent(maz_search *s, const maz_search_call *c, bool recor
     maz_infer_desc &d = P.d;
     d.B = B; d.Nt = s->Nt; d.cur = seq ? c->cur : -1; d.inv_tau = 1.0f / c->tau;
     d.pool = s->pool; d.next_hidden = s->pool + (size_t)B * s->D;
-    d.idx_x = record ? s->rec_ix : s->idx_x;
-    d.actions = record ? s->rec_act : s->act;
-    d.reward = record ? s->rec_r : s->sim_r; d.value = record ? s->rec_v : s->sim_v;
-    d.probs = record ? s->rec_p : s->sim_p; d.beta = record ? s->rec_b : s->sim_b;
+    d.idx_x = nullptr; d.actions = nullptr;              // (the exchange arrays live in the kernel's shared memory)
+    d.reward = d.value = d.probs = d.beta = nullptr;
     d.greedy = nullptr; d.logits_out = nullptr; d.dbg_clock = nullptr;
     d.roots_per_tile = s->rpt;
     d.factor = seq ? s->factor : nullptr;
@@ -425,12 +435,13 @@ static int launch_persistent(maz_search *s, const maz_search_call *c, bool recor
     P.g_err = t->d_err;
     P.idx_y = s->idx_y;
     P.greedy_w = seq ? s->greedy : nullptr;
-    P.rec = record ? 1 : 0;
+    if (record) { P.rec_r = s->rec_r; P.rec_v = s->rec_v; P.rec_p = s->rec_p; P.rec_b = s->rec_b; P.rec_ix = s->rec_ix; P.rec_act = s->rec_act; }
     P.tree_clock = s->dbg_clock;
     const unsigned grid = (unsigned)((B + s->rpt - 1) / s->rpt);
-    persist::k_search_persistent<<<grid, hmma::NTHREADS, hmma::smem_bytes(s->sm.vec_floats), s->stream>>>(P);
+    const size_t dyn = persist::persist_smem_bytes(s->sm.vec_floats, s->rpt, s->Nt, s->cfg.A, s->cfg.S);
+    if (P.tree_clock != nullptr) persist::k_search_persistent<true><<<grid, persist::PERSIST_THREADS, dyn, s->stream>>>(P);
+    else persist::k_search_persistent<false><<<grid, persist::PERSIST_THREADS, dyn, s->stream>>>(P);
     CU_TRY(cudaGetLastError());
-    (void)N;
     return MAZ_OK;
 }
 

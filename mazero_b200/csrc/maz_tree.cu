@@ -105,7 +105,7 @@ static int build_layout(TreeLayout &L, int B, int N, int A, int K, int S, float 
         // nodes (~4 k cycles per 32 of them).  MAZ_SELECT_WIDE=0 never, 1 always (tests run both: identical results).
         const char *e = getenv("MAZ_SELECT_WIDE");
         const int chunks = (S + 1 + 31) / 32;
-        L.wide_min_len = e ? (atoi(e) ? 0 : 1 << 30) : 2 + 2 * chunks;
+        L.wide_min_len = e ? (atoi(e) ? 0 : 1 << 30) : 3 + 2 * chunks;
     }
     L.slab_bytes = align_up(o, 256);
     if (o > 0xfffffff0ull) return set_err(MAZ_ERR_UNSUPPORTED, "per-tree slab exceeds 4 GiB");

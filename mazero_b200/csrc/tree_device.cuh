@@ -89,6 +89,21 @@ __device__ __forceinline__ void rec_store_new_child(const TreeLayout &L, char *t
 
 __device__ __forceinline__ TreeHdr *f_hdr(char *tb) { return reinterpret_cast<TreeHdr *>(tb); }
 
+struct TreeHot;
+// The tree's small, hot bookkeeping arrays.  The stand-alone kernels use them where they live in the slab (global memory); the
+// persistent whole-search kernel keeps a copy of them -- and of the header -- in shared memory for the whole search, because the
+// warp that owns the tree touches them in every phase of every simulation (each access was an L2 round trip on the critical path).
+struct TreeHot {
+    uint16_t *path;      // [S + 2] SearchResult::search_path (node slots)
+    float *qd;           // [S + 2] q-delta entries of the expanded nodes (CMinMaxStats)
+    uint16_t *expslot;   // [S + 2] slot of the e-th expanded node
+    uint16_t *depth;     // [S + 2] its depth
+};
+__device__ __forceinline__ TreeHot hot_from_slab(const TreeLayout &L, char *tb)
+{
+    return TreeHot{f_path(L, tb), f_qdelta(L, tb), f_expslot(L, tb), f_depth(L, tb)};
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
 // may start while its predecessor in the stream is still running; griddep_wait() blocks until the predecessor has
 // completed and its writes are visible (a no-op without the attribute); griddep_launch() lets the successor start.
@@ -246,7 +261,18 @@ __device__ __forceinline__ ExpandScratch carve_scratch(char *p, int N, int A)
 // Samples K joint actions from the factorised per-agent distribution beta, merges duplicates, creates
 // the children in ascending (wrapped, signed 64-bit) key order in consecutive slots.  Returns the number
 // of children.  `probs`, `beta`, `noises` point at this tree's (N,A) rows in global memory.
-__device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &tot_nodes, int &n_expanded, int &mt_pos,
+// kCg: read the network outputs with ld.global.cg (L2): they are produced by another kernel that, under programmatic dependent
+// launch, may still be running when this one becomes resident (stale L1 lines of the re-used buffers).  false: plain generic loads
+// (the persistent kernel hands them over in shared memory).
+template <bool kCg = true>
+__device__ __forceinline__ float ld_in(const float *p)
+{
+    if (kCg) return __ldcg(p);
+    return *p;
+}
+
+template <bool kCg = true>
+__device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, const TreeHot &hot, int &tot_nodes, int &n_expanded, int &mt_pos,
                                            int &err, int slot, int hidx, float reward, float value,
                                            const float *__restrict__ probs, const float *__restrict__ beta,
                                            int K, float eps, const float *__restrict__ noises,
@@ -258,8 +284,8 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
     // .cg loads (L2 only): under programmatic dependent launch this kernel can already be resident on an SM whose
     // L1 still holds the previous simulation's lines of these (re-used) buffers
     for (int t = lane; t < NA; t += 32) {
-        sc.beta[t] = __ldcg(beta + t);
-        sc.probs[t] = __ldcg(probs + t);
+        sc.beta[t] = ld_in<kCg>(beta + t);
+        sc.probs[t] = ld_in<kCg>(probs + t);
     }
     __syncwarp();
     MAZ_TS(L, dbg_tree, lane, 11);
@@ -376,7 +402,7 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
             beta_prob = __fmul_rn(beta_prob, pb);
             pred_prob = __fmul_rn(pred_prob, pp);
             if (eps > 0) {
-                float p = __fadd_rn(__fmul_rn(pp, ome), __fmul_rn(__ldcg(noises + i * A + a), eps));
+                float p = __fadd_rn(__fmul_rn(pp, ome), __fmul_rn(ld_in<kCg>(noises + i * A + a), eps));
                 prior = __fmul_rn(prior, p);
             } else {
                 prior = __fmul_rn(prior, pp);
@@ -399,8 +425,8 @@ __device__ __forceinline__ int expand_node(const TreeLayout &L, char *tb, int &t
             f_wsum(L, tb)[slot] = 0.0f;
             f_wtot(L, tb)[slot] = 0.0f;
         }
-        f_expslot(L, tb)[n_expanded] = (uint16_t)slot;
-        f_depth(L, tb)[n_expanded] = (uint16_t)depth;
+        hot.expslot[n_expanded] = (uint16_t)slot;
+        hot.depth[n_expanded] = (uint16_t)depth;
         f_eid(L, tb)[slot] = (uint16_t)n_expanded;   // expansion order: index of this node's q-delta entry
     }
     tot_nodes = base + C;

@@ -72,7 +72,7 @@ __global__ void k_prepare(TreeLayout L, char *arena, const float *__restrict__ l
     }
     const size_t NA = (size_t)L.N * L.A;
     const float value = values[tree];
-    expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, 0, 0, rewards[tree], value, probs + tree * NA,
+    expand_node(L, tb, hot_from_slab(L, tb), tot_nodes, n_expanded, mt_pos, err, 0, 0, rewards[tree], value, probs + tree * NA,
                 beta + tree * NA, K, eps, noises + tree * NA, sc, lane);
     float ws = 0.0f, wt = 0.0f;
     vs_update(L, tb, log_len, err, ws, wt, 0, 0, value, lam_pow, lane);  // root.subtree_info.update(value, 0)
@@ -101,7 +101,7 @@ __global__ void k_select(TreeLayout L, char *arena, const float *__restrict__ lo
     int tree, lane;
     if (!warp_tree(L, tree, lane)) return;
     char *tb = arena + (size_t)tree * L.slab_bytes;
-    select_path_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
+    select_path_device(L, tb, f_hdr(tb), hot_from_slab(L, tb), logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
 }
 
 __global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restrict__ lam_pow, int hidx, float discount,
@@ -114,7 +114,7 @@ __global__ void k_expand_backup(TreeLayout L, char *arena, const float *__restri
     char *tb = arena + (size_t)tree * L.slab_bytes;
     const StepScratch scr = carve_step_scratch(smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K, L.S), L.N, L.A, L.K, L.S);
     const size_t NA = (size_t)L.N * L.A;
-    expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
+    expand_backup_device(L, tb, f_hdr(tb), hot_from_slab(L, tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
                          beta + tree * NA, scr, lane, g_err);
 }
 
@@ -132,10 +132,10 @@ __global__ void k_expand_backup_select(TreeLayout L, char *arena, const float *_
     char *tb = arena + (size_t)tree * L.slab_bytes;
     const StepScratch scr = carve_step_scratch(smem + (size_t)(threadIdx.x >> 5) * tree_scratch_bytes(L.N, L.A, L.K, L.S), L.N, L.A, L.K, L.S);
     const size_t NA = (size_t)L.N * L.A;
-    expand_backup_device(L, tb, f_hdr(tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
+    expand_backup_device(L, tb, f_hdr(tb), hot_from_slab(L, tb), lam_pow, hidx, discount, K, rewards + tree, values + tree, probs + tree * NA,
                          beta + tree * NA, scr, lane, g_err, tree);
     __syncwarp();
-    select_next_device(L, tb, f_hdr(tb), logterm, sqrtn, table_len, discount, tree, lane, &scr, idx_x, idx_y, act_out, g_err);
+    select_next_device(L, tb, f_hdr(tb), hot_from_slab(L, tb), logterm, sqrtn, table_len, discount, tree, lane, &scr, idx_x, idx_y, act_out, g_err);
     MAZ_TS(L, tree, lane, 6);
 }
 
@@ -179,7 +179,7 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
             mt_pos += n_draw;
         }
         griddep_wait();
-        expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, __ldcg(rewards + tree), __ldcg(values + tree),
+        expand_node(L, tb, hot_from_slab(L, tb), tot_nodes, n_expanded, mt_pos, err, leaf, hidx, __ldcg(rewards + tree), __ldcg(values + tree),
                     probs + tree * NA, beta + tree * NA, K, 0.0f, nullptr, sc, lane, draws_pre, -1, /*init_stats=*/false, /*depth=*/len);
         if (lane == 0) {
             h->tot_nodes = tot_nodes;
@@ -195,10 +195,10 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
         log_prefetch(L, tb, log_len0, lane, lr);
         griddep_wait();
         const float reward_in = __ldcg(rewards + tree), value = __ldcg(values + tree);
-        backup_parallel(L, tb, lam_pow, scr, lr, f_path(L, tb), len, log_len0, n_exp0, reward_in, value, discount, lane, log_len, err);
+        backup_parallel(L, tb, hot_from_slab(L, tb), lam_pow, scr, lr, len, log_len0, n_exp0, reward_in, value, discount, lane, log_len, err);
         const int n_exp1 = n_exp0 + 1;
         float mn, mx;
-        minmax_reduce(L, tb, n_exp1, lane, mn, mx);
+        minmax_reduce(hot_from_slab(L, tb), n_exp1, lane, mn, mx);
         if (lane == 0) {
             h->log_len = log_len;
             h->mm_cnt = n_exp1 - 1;
@@ -211,7 +211,7 @@ __global__ void k_expand_backup_select2(TreeLayout L, char *arena, const float *
     __syncthreads();   // expansion and backup of every tree of the block are complete and visible
     const long long t2 = dbg ? clock64() : 0;
     if (active && role == 0)
-        select_next_device(L, tb, h, logterm, sqrtn, table_len, discount, tree, lane, &scr, idx_x, idx_y, act_out, g_err);
+        select_next_device(L, tb, h, hot_from_slab(L, tb), logterm, sqrtn, table_len, discount, tree, lane, &scr, idx_x, idx_y, act_out, g_err);
     if (dbg && role == 0) {
         dbg[2] = clock64() - t2;
         dbg[3] = len;

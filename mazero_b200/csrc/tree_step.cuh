@@ -73,12 +73,12 @@ __device__ __forceinline__ float ucb_score_device(const TreeLayout &L, const flo
 // Sequential form: latency-bound pointer chase, ONE memory round trip per tree level.  While the children of the current node are
 // scored (one lane per child), each child's own header is already in its lane's registers, so descending is a shuffle.  The
 // next few mt19937 outputs are prefetched at the start (one raw draw per select_child call).
-__device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ logterm,
+__device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb, TreeHdr *h, const TreeHot &hot, const float *__restrict__ logterm,
                                                    const double *__restrict__ sqrtn, int table_len, float discount, int tree,
                                                    int lane, int *__restrict__ idx_x, int *__restrict__ idx_y,
                                                    int *__restrict__ act_out, int *g_err)
 {
-    uint16_t *path = f_path(L, tb);
+    uint16_t *path = hot.path;
     uint32_t *mt = f_mt(L, tb);
 
     // round trip 0: tree header, root header, prefetched random words
@@ -173,7 +173,7 @@ __device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb
         h->mt_pos = mt_pos;
         h->sum_path_len += len;
         idx_x[tree] = parent_hidx;
-        idx_y[tree] = tree;
+        if (idx_y) idx_y[tree] = tree;
         if (err) {
             h->err = err;
             *g_err = err;
@@ -189,7 +189,8 @@ __device__ __forceinline__ void select_path_device(const TreeLayout &L, char *tb
 // 373-377).  So all choices are made at once (children scored sequentially inside the lane: literally the reference's loop,
 // cnode.cpp:351-370), and the path is then a pointer chase through a shared-memory table.  Returns false, having changed
 // nothing, when the words needed straddle the end of the generator's block (the sequential form regenerates it on the way).
-__device__ __forceinline__ bool select_path_wide(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ logterm,
+// (out of line: rare, large; the sequential form and the backup stay inlined in their kernels)
+static __device__ __noinline__ bool select_path_wide(const TreeLayout &L, char *tb, TreeHdr *h, const TreeHot &hot, const float *__restrict__ logterm,
                                                  const double *__restrict__ sqrtn, int table_len, float discount, int tree, int lane,
                                                  const StepScratch &scr, int *__restrict__ idx_x, int *__restrict__ idx_y,
                                                  int *__restrict__ act_out, int *g_err)
@@ -199,56 +200,89 @@ __device__ __forceinline__ bool select_path_wide(const TreeLayout &L, char *tb, 
     const float mn = h->mm_min, mx = h->mm_max;
     const int mmc = h->mm_cnt;
     const uint32_t *mt = f_mt(L, tb);
-    const uint16_t *expslot = f_expslot(L, tb);
-    const uint16_t *depth = f_depth(L, tb);
+    const uint16_t *expslot = hot.expslot;
+    const uint16_t *depth = hot.depth;
     const RecRegs root = rec_load(L, tb, 0);
     const int forced = (rec_visit(root) <= rec_nchild(root)) ? 1 : 0;
+    // NPL nodes per lane and pass, children in batches of CB: every load of a batch (CB x 32 bytes per lane and node) is in flight
+    // before the first score is computed -- a pass is a handful of L2 round trips, not one per child.  (NPL = 2 spills registers
+    // next to the inference stages' 160+; NPL = 1 with 5-child batches does not.)
+    constexpr int NPL = 1, CB = 5;
 #pragma unroll 1
-    for (int e0 = 0; e0 < n_exp; e0 += 32) {
-        const int e = e0 + lane;
-        if (e < n_exp) {
-            const int slot = expslot[e], dep = depth[e];
-            const RecRegs nr = rec_load(L, tb, slot);
-            const int C = rec_nchild(nr), base = rec_cbase(nr), vc = rec_visit(nr);
-            const float pq = rec_pred_value(nr);
-            int ci;
-            if (e == 0 && forced) {
-                ci = vc - 1;
-            } else {
-                const uint32_t word = mt[mt_pos + dep - forced];
-                int n = vc - 1;
-                if (n >= table_len) n = table_len - 1;
-                float max_score = -1000000.0f;               // FLOAT_MIN (utils.h:11-12)
-                unsigned listmask = 0;
-#pragma unroll 2
-                for (int c = 0; c < C; ++c) {
-                    const RecRegs r = rec_load(L, tb, base + c);
-                    const float s = ucb_score_device(L, logterm, sqrtn, n, discount, pq, mn, mx, mmc, rec_prior(r), rec_visit(r),
-                                                     rec_reward(r), rec_wsum(r), rec_wtot(r));
-                    if (max_score < s) {
-                        max_score = s;
-                        listmask = 1u << c;
-                    } else if (s >= __fsub_rn(max_score, 0.000001f)) {
-                        listmask |= 1u << c;
+    for (int e0 = 0; e0 < n_exp; e0 += 32 * NPL) {
+        int slot[NPL], C[NPL], base[NPL], n[NPL], dep[NPL];
+        float pq[NPL], max_score[NPL];
+        unsigned listmask[NPL];
+        uint32_t word[NPL];
+        bool on[NPL], draw[NPL];
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {
+            const int e = e0 + 32 * u + lane;
+            on[u] = e < n_exp;
+            slot[u] = on[u] ? expslot[e] : 0;
+            dep[u] = on[u] ? depth[e] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {
+            const int e = e0 + 32 * u + lane;
+            const RecRegs nr = rec_load(L, tb, slot[u]);
+            C[u] = on[u] ? rec_nchild(nr) : 0;
+            base[u] = rec_cbase(nr);
+            const int vc = rec_visit(nr);
+            pq[u] = rec_pred_value(nr);
+            draw[u] = on[u] && !(e == 0 && forced);
+            word[u] = draw[u] ? mt[mt_pos + dep[u] - forced] : 0u;
+            n[u] = min(vc - 1, table_len - 1);
+            max_score[u] = -1000000.0f;                      // FLOAT_MIN (utils.h:11-12)
+            listmask[u] = 0u;
+            if (on[u] && !draw[u]) listmask[u] = 1u << (vc - 1);   // forced root round-robin (no draw): the only candidate
+        }
+        int Cmax = 0;
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) Cmax = max(Cmax, draw[u] ? C[u] : 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < Cmax; c0 += CB) {
+            RecRegs r[NPL][CB];
+#pragma unroll
+            for (int u = 0; u < NPL; ++u)
+#pragma unroll
+                for (int j = 0; j < CB; ++j)
+                    if (draw[u] && c0 + j < C[u]) r[u][j] = rec_load(L, tb, base[u] + c0 + j);
+#pragma unroll
+            for (int u = 0; u < NPL; ++u)
+#pragma unroll
+                for (int j = 0; j < CB; ++j)
+                    if (draw[u] && c0 + j < C[u]) {          // the reference's loop body (cnode.cpp:354-369), child c0 + j
+                        const float sc = ucb_score_device(L, logterm, sqrtn, n[u], discount, pq[u], mn, mx, mmc, rec_prior(r[u][j]),
+                                                          rec_visit(r[u][j]), rec_reward(r[u][j]), rec_wsum(r[u][j]), rec_wtot(r[u][j]));
+                        if (max_score[u] < sc) {
+                            max_score[u] = sc;
+                            listmask[u] = 1u << (c0 + j);
+                        } else if (sc >= __fsub_rn(max_score[u], 0.000001f)) {
+                            listmask[u] |= 1u << (c0 + j);
+                        }
                     }
-                }
-                const int nl = __popc(listmask);
-                ci = 0;
-                if (nl > 0) {
-                    uint32_t mrem = listmask;
-                    for (uint32_t skip = mt_temper(word) % (uint32_t)nl; skip > 0; --skip) mrem &= mrem - 1;
-                    ci = __ffs(mrem) - 1;
-                }
+        }
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {
+            if (!on[u]) continue;
+            int ci = 0;
+            const int nl = __popc(listmask[u]);
+            if (nl > 0) {
+                uint32_t mrem = listmask[u];
+                if (draw[u])                                 // one raw word per select_child call, even for a single candidate
+                    for (uint32_t skip = mt_temper(word[u]) % (uint32_t)nl; skip > 0; --skip) mrem &= mrem - 1;
+                ci = __ffs(mrem) - 1;
             }
-            const int cs = base + ci;
+            const int cs = base[u] + ci;
             const RecRegs cr = rec_load(L, tb, cs);          // (just scored: L1)
             const int ceid = (rec_nchild(cr) > 0) ? rec_eid(cr) + 1 : 0;      // expanded() = num_children > 0
-            scr.chase[e] = ((uint32_t)cs << 16) | (uint32_t)ceid;
+            scr.chase[e0 + 32 * u + lane] = ((uint32_t)cs << 16) | (uint32_t)ceid;
         }
     }
     __syncwarp();
     // the path: root -> chosen child -> ... until an unexpanded node
-    uint16_t *path = f_path(L, tb);
+    uint16_t *path = hot.path;
     int e = 0, len = 0, node = 0, parent = 0, err = 0;
     if (lane == 0) path[0] = 0;
     while (true) {
@@ -270,7 +304,7 @@ __device__ __forceinline__ bool select_path_wide(const TreeLayout &L, char *tb, 
         h->mt_pos = mt_pos + len - forced;                   // one word per select_child call
         h->sum_path_len += len;
         idx_x[tree] = f_hidx(L, tb)[parent];                 // hidden_state_index_x of the leaf's parent
-        idx_y[tree] = tree;
+        if (idx_y) idx_y[tree] = tree;
         if (err) {
             h->err = err;
             *g_err = err;
@@ -282,15 +316,15 @@ __device__ __forceinline__ bool select_path_wide(const TreeLayout &L, char *tb, 
 }
 
 // the selection of the next simulation: wide when the last path was long (scr may be NULL: sequential only)
-__device__ __forceinline__ void select_next_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ logterm,
+__device__ __forceinline__ void select_next_device(const TreeLayout &L, char *tb, TreeHdr *h, const TreeHot &hot, const float *__restrict__ logterm,
                                                    const double *__restrict__ sqrtn, int table_len, float discount, int tree,
                                                    int lane, const StepScratch *scr, int *__restrict__ idx_x, int *__restrict__ idx_y,
                                                    int *__restrict__ act_out, int *g_err)
 {
     if (scr != nullptr && h->path_len >= L.wide_min_len &&
-        select_path_wide(L, tb, h, logterm, sqrtn, table_len, discount, tree, lane, *scr, idx_x, idx_y, act_out, g_err))
+        select_path_wide(L, tb, h, hot, logterm, sqrtn, table_len, discount, tree, lane, *scr, idx_x, idx_y, act_out, g_err))
         return;
-    select_path_device(L, tb, h, logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
+    select_path_device(L, tb, h, hot, logterm, sqrtn, table_len, discount, tree, lane, idx_x, idx_y, act_out, g_err);
 }
 
 // ---- CTree::back_propagate (cnode.cpp:415-450), shared by every kernel --------------------------------------------------
@@ -337,13 +371,14 @@ __device__ __forceinline__ void backup_scatter_entry(const StepScratch &scr, int
 // order the leaf gets in this simulation; reward_in / value = this simulation's network outputs; `lr` = the first 256 entries of
 // the log as they were BEFORE this backup.  Writes visit / wsum / wtot of every path node (the leaf's included), the q-delta
 // entries and the log appends.  Warp-uniform log_len / err.
-__device__ __forceinline__ void backup_parallel(const TreeLayout &L, char *tb, const float *__restrict__ lam_pow, const StepScratch &scr,
-                                                const LogRegs &lr, const uint16_t *__restrict__ path, int len, int log_len0, int leaf_eid,
+__device__ __forceinline__ void backup_parallel(const TreeLayout &L, char *tb, const TreeHot &hot, const float *__restrict__ lam_pow,
+                                                const StepScratch &scr, const LogRegs &lr, int len, int log_len0, int leaf_eid,
                                                 float reward_in, float value, float discount, int lane, int &log_len, int &err)
 {
     uint32_t *vk = f_vskey(L, tb);
     float *vv = f_vsval(L, tb);
-    float *qd = f_qdelta(L, tb);                      // q-delta of the e-th expanded node (the CMinMaxStats entries)
+    float *qd = hot.qd;                               // q-delta of the e-th expanded node (the CMinMaxStats entries)
+    const uint16_t *path = hot.path;
     // ---- pass over the log: every entry is looked at once -----------------------------------------------------------------
     for (int i = lane; i <= len; i += 32) {
         scr.pathc[i] = path[i];
@@ -422,9 +457,9 @@ __device__ __forceinline__ void backup_parallel(const TreeLayout &L, char *tb, c
 }
 
 // CMinMaxStats min / max = reduction over the q-deltas of all visited (= expanded) non-root nodes [1, n_expanded)
-__device__ __forceinline__ void minmax_reduce(const TreeLayout &L, char *tb, int n_expanded, int lane, float &mn, float &mx)
+__device__ __forceinline__ void minmax_reduce(const TreeHot &hot, int n_expanded, int lane, float &mn, float &mx)
 {
-    const float *qd = f_qdelta(L, tb);
+    const float *qd = hot.qd;
     uint32_t lo = 0xffffffffu, hi = 0u;
     for (int e = 1 + lane; e < n_expanded; e += 32) {
         const uint32_t o = f2ord(qd[e]);
@@ -438,7 +473,8 @@ __device__ __forceinline__ void minmax_reduce(const TreeLayout &L, char *tb, int
 // ---- CTree_batch::cbatch_expansion_and_backup -> expand_and_backprop (cnode.cpp:644-670, 452-469), ONE warp per tree ------
 // Latency plan: everything that depends only on the tree's own state (header, log snapshot, the expansion's random words) is
 // requested before the network outputs are needed.
-__device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *tb, TreeHdr *h, const float *__restrict__ lam_pow,
+template <bool kCg = true>
+__device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *tb, TreeHdr *h, const TreeHot &hot, const float *__restrict__ lam_pow,
                                                      int hidx, float discount, int K, const float *__restrict__ reward_ptr,
                                                      const float *__restrict__ value_ptr,
                                                      const float *__restrict__ probs, const float *__restrict__ beta,
@@ -460,20 +496,19 @@ __device__ __forceinline__ void expand_backup_device(const TreeLayout &L, char *
         for (int t = lane; t < n_draw; t += 32) scr.ex.draws[t] = mt_temper(mt[mt_pos + t]);
         mt_pos += n_draw;
     }
-    const uint16_t *path = f_path(L, tb);
-    const int leaf = path[len];
+    const int leaf = hot.path[len];
     MAZ_TS(L, tree, lane, 2);
     // PDL: everything above only touched this tree's own state (written by the previous tree kernel, long
     // complete); the network outputs of THIS simulation are produced by the kernel we may be overlapping with.
     griddep_wait();
-    const float reward_in = __ldcg(reward_ptr), value = __ldcg(value_ptr);   // L2 loads, see expand_node
-    expand_node(L, tb, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, reward_in, value, probs, beta, K, 0.0f, nullptr, scr.ex,
-                lane, draws_pre, tree, /*init_stats=*/true, /*depth=*/len);
+    const float reward_in = ld_in<kCg>(reward_ptr), value = ld_in<kCg>(value_ptr);   // (L2 loads, see expand_node)
+    expand_node<kCg>(L, tb, hot, tot_nodes, n_expanded, mt_pos, err, leaf, hidx, reward_in, value, probs, beta, K, 0.0f, nullptr, scr.ex,
+                     lane, draws_pre, tree, /*init_stats=*/true, /*depth=*/len);
     MAZ_TS(L, tree, lane, 3);
-    backup_parallel(L, tb, lam_pow, scr, lr, path, len, log_len0, leaf_eid, reward_in, value, discount, lane, log_len, err);
+    backup_parallel(L, tb, hot, lam_pow, scr, lr, len, log_len0, leaf_eid, reward_in, value, discount, lane, log_len, err);
     MAZ_TS(L, tree, lane, 4);
     float mn, mx;
-    minmax_reduce(L, tb, n_expanded, lane, mn, mx);
+    minmax_reduce(hot, n_expanded, lane, mn, mx);
     if (lane == 0) {
         h->tot_nodes = tot_nodes;
         h->log_len = log_len;

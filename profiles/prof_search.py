@@ -30,7 +30,7 @@ def main():
         times = []
         rpc = max(1, min(8, 32 // N, int(os.environ.get("MAZ_SEARCH_RPT", "8"))))
         ncta = (B + rpc - 1) // rpc
-        clk = torch.zeros(2 * S + 4 * ncta + 64 + 4 * B, dtype=torch.int64, device=dev)
+        clk = torch.zeros(2 * S + 4 * ncta + 64 + 4 * B + 32, dtype=torch.int64, device=dev)
         if plan.native is not None and plan.native.strategy == "persistent":
             plan.native.set_debug_clock(clk)
         for r in range(reps + 2):
@@ -71,7 +71,19 @@ def main():
                 m = (d >= lo) & (d < hi)
                 if m.any():
                     print(f"    mean depth in [{lo},{hi}): {m.sum()} trees, expand+backup {pt[m, 0].mean() / S:.0f}, select {pt[m, 1].mean() / S:.0f} cycles/sim")
-        st = call[2 * S + 4 * ncta:][:64]
+        ts = call[2 * S + 4 * ncta + 64 + 4 * B:][:32]
+        if ts[:6].all():
+            nm = {0: "start", 1: "header", 2: "prefetch issued", 11: "beta/probs staged", 12: "cdf", 13: "sampled", 14: "keys merged",
+                  15: "children", 3: "expansion done", 4: "backup", 5: "minmax+header"}
+            order = [0, 1, 2, 11, 12, 13, 14, 15, 3, 4, 5]
+            print("  tree 0, phase cycles per simulation (mean over the search): " +
+                  ", ".join(f"{nm[b]} {ts[16 + i + 1] / S:.0f}" for i, b in enumerate(order[1:])))
+        st_all = call[2 * S + 4 * ncta:][:64]
+        hs = st_all[40:]
+        hs = hs[hs > 0]
+        if len(hs) > 2:
+            print("  heads2 phases (cycles): " + " ".join(str(int(v)) for v in np.diff(hs)))
+        st = st_all[:40]
         st = st[st > 0]
         if len(st) > 2:
             names = ["gather", "sync", "inproj"] + [f"L{l}.{x}" for l in range(3) for x in ("qkv", "attn", "out+ln", "lin1", "lin2+ln")] + \
