@@ -617,7 +617,7 @@ def run_ours(args):
         "warmup": warm, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong" if args.total_roots else "weak",
         "vs_baseline": None, "dtype": "bf16" if inf.fused is not None else "f32", "data": "synthetic",
         "config": config_dict(args, N, A, B, S, K),
-        "details": {"tree_agents": prob.Nt if "prob" in dir() else None, "inference": inf.mode, "search_strategy": strategy,
+        "details": {"tree_agents": N if cur is None else 1, "inference": inf.mode, "search_strategy": strategy,
                     "l2": "flushed (256 MiB memset) between timed steps",
                     "inputs": "5 synthetic batches of root hidden states rotated per step (rank offset)",
                     "legal_mask": args.legal_frac or "all legal", "mean_search_depth": dbar, "mean_children": cbar,

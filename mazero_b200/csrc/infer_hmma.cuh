@@ -886,15 +886,19 @@ static __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring, cons
     }
     HS();
     if (tid < TM * 8) {   // policy outputs: 8 threads per row (softmax, beta, greedy); warp-uniform condition
+        // every thread keeps its (at most 6) logits in registers: one batch of loads, two 8-lane reductions, one batch of stores
+        constexpr int PA = 6;                                          // actions per thread: A <= 48
         const int r = tid >> 3, sub = tid & 7;
         const RowInfo ri = row_info(r);
         const uint32_t lg = PL + 4u * (r * 48);
+        float v[PA];
+#pragma unroll
+        for (int i = 0; i < PA; ++i) v[i] = (sub + 8 * i < A) ? lds1v(lg + 4u * (sub + 8 * i)) : -INFINITY;
         float m = -INFINITY;
         int am = 0x7fffffff;
-        for (int a = sub; a < A; a += 8) {
-            const float v = lds1v(lg + 4u * a);
-            if (v > m) { m = v; am = a; }
-        }
+#pragma unroll
+        for (int i = 0; i < PA; ++i)
+            if (v[i] > m) { m = v[i]; am = sub + 8 * i; }
 #pragma unroll
         for (int o = 1; o <= 4; o <<= 1) {
             const float om = __shfl_xor_sync(0xffffffffu, m, o);
@@ -903,11 +907,13 @@ static __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring, cons
         }
         HS();
         const bool unit_tau = (d.inv_tau == 1.0f);
-        float s = 0.f, sbeta = 0.f;
-        for (int a = sub; a < A; a += 8) {
-            const float e = __expf(lds1v(lg + 4u * a) - m);
-            s += e;
-            sbeta += unit_tau ? e : __powf(e, d.inv_tau);
+        float e[PA], eb[PA], s = 0.f, sbeta = 0.f;
+#pragma unroll
+        for (int i = 0; i < PA; ++i) {
+            e[i] = (sub + 8 * i < A) ? __expf(v[i] - m) : 0.f;
+            eb[i] = unit_tau ? e[i] : ((sub + 8 * i < A) ? __powf(e[i], d.inv_tau) : 0.f);
+            s += e[i];
+            sbeta += eb[i];
         }
 #pragma unroll
         for (int o = 1; o <= 4; o <<= 1) {
@@ -919,14 +925,16 @@ static __device__ __noinline__ void stage_heads2(const Desc &d, Ring &ring, cons
             if (io.greedy && sub == 0) io.greedy[(size_t)ri.root * N + ri.agent] = am;
             const int ta = (d.cur < 0) ? ri.agent : (ri.agent == d.cur ? 0 : -1);
             const float invs = 1.f / s, invb = 1.f / sbeta;
-            for (int a = sub; a < A; a += 8) {
-                const float v = lds1v(lg + 4u * a);
-                if (io.logits_out) io.logits_out[((size_t)ri.root * N + ri.agent) * A + a] = v;
-                if (ta >= 0) {
-                    const float e = __expf(v - m);
-                    const size_t o = ((size_t)(ri.root - io.root0) * d.Nt + ta) * A + a;
-                    io.probs[o] = e * invs;
-                    io.beta[o] = (unit_tau ? e : __powf(e, d.inv_tau)) * invb;
+#pragma unroll
+            for (int i = 0; i < PA; ++i) {
+                const int a = sub + 8 * i;
+                if (a < A) {
+                    if (io.logits_out) io.logits_out[((size_t)ri.root * N + ri.agent) * A + a] = v[i];
+                    if (ta >= 0) {
+                        const size_t o = ((size_t)(ri.root - io.root0) * d.Nt + ta) * A + a;
+                        io.probs[o] = e[i] * invs;
+                        io.beta[o] = eb[i] * invb;
+                    }
                 }
             }
         }

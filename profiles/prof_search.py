@@ -31,8 +31,8 @@ def main():
         rpc = max(1, min(8, 32 // N, int(os.environ.get("MAZ_SEARCH_RPT", "8"))))
         ncta = (B + rpc - 1) // rpc
         clk = torch.zeros(2 * S + 4 * ncta + 64 + 4 * B + 32, dtype=torch.int64, device=dev)
-        if plan.native is not None and plan.native.strategy == "persistent":
-            plan.native.set_debug_clock(clk)
+        if plan.native is not None and plan.native.strategy == "persistent" and not os.environ.get("MAZ_NO_CLOCK"):
+            plan.native.set_debug_clock(clk)      # (selects the kernel instance with the in-kernel cycle counters)
         for r in range(reps + 2):
             h = root_hidden(B, N, seed=r % 5).to(dev)
             pol, vlog = inf.prediction(h)
