@@ -346,7 +346,8 @@ class _DevicePlan:
                 self._arm_record()
             self.native.run_dev(cur, seed, cfg, noise_eps, self.tau, self.root_r, self.root_v, self.inp["logits"],
                                 self.inp["legal"] if self.has_legal else None, self.inp[f"noise_raw{slot}"],
-                                self.factor if cur else None, self.turn_out[slot], root_index_offset=root_index_offset)
+                                self.factor if cur else None, self.turn_out[slot], root_index_offset=root_index_offset,
+                                cache_key=(slot, bool(cur), self.has_legal))
             return
         ptr = lambda t: C.c_void_p(t.data_ptr())
         check(lib.maz_root_prepare_dev(                                         # mcts_sampled.py:57-106 on the device
