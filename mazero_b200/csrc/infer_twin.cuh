@@ -1,0 +1,745 @@
+// infer_twin.cuh -- the large-batch recurrent_inference kernel, second generation (sm_100a): TWO 128-row tiles in flight per CTA.
+//
+// Same computation as infer_fused.cuh (config/smac/model.py:562-574 = dynamics :251-282 with attention.py:27-43, prediction
+// :335-373, GraphNetNN :136-174; inverse support transform core/config.py:430-442,463-499; the driver's softmax / beta
+// mcts_sampled.py:158-161), restructured around what bounded the first kernel at 2s3z / MMM2 / 27m batch sizes
+// (profiles/r01_ncu_summary.md): one tile per CTA walks 25 dependent stages, and in every stage the tensor pipe waits for the
+// epilogue warps and the epilogue warps for the tensor pipe (MMA + hand-offs were ~1/3 of a tile's time); and the attention
+// over the agent axis was scalar code whose cost grew with the team size (27m: about half of the tile time).
+//
+//   * Ping-pong: a CTA owns tiles A and B.  The 16 epilogue warps alternate epi A(s), epi B(s), epi A(s+1), ...; the MMA warp
+//     issues stage s+1 of a tile as soon as that tile's epilogue s has published its operands, i.e. WHILE the epilogue warps
+//     work on the other tile.  tcgen05.mma execution, commit -> wait latency and the barrier hand-off of one tile hide behind
+//     the other tile's epilogue.
+//   * TMEM: 256 columns per tile (ACC0 | ACC1).  The fp32 residual stream of the first kernel (128 more columns per tile) is
+//     gone: x lives only as the bf16 operand tile and `x + f(x)` is added in the epilogue from that tile.
+//   * q|k|v is two stages: V first (drained as bf16 into the tile that will receive the attention output), then Q|K.
+//   * Attention over the agents of a root on warp-level tensor-core MMAs (mma.sync.m16n8k16, bf16): a warp holds 32 token
+//     rows (whole roots) and two heads; S = Q K^T (32 x 32 x 16) with a block-diagonal root mask, softmax on the accumulator
+//     fragments, O = P V (32 x 16 x 32).  The tcgen05 operand layout is made of 8 x 16-byte core matrices, which is exactly
+//     what ldmatrix reads: V fragments come straight from the operand tile (ldmatrix.trans).  16 MMAs per head and warp
+//     whatever the team size (the scalar loop was ~110 instructions per key, head and row).
+//   * The one-hot joint-action operand is gone: `W [h | onehot(a)]` = `W_h h + W_a[:, a]`, the column is added in the epilogue
+//     from an fp32 table (three fewer MMA groups, no one-hot tiles in shared memory).
+//   * Weights stream through a 4 x 16 KB ring in K-halves (a 128 x 128 matrix is two pieces); slots are released by
+//     tcgen05.commit from the MMA warp.  Biases / LayerNorm affines / heads are read from global memory (L1-resident):
+//     shared memory holds 4 operand tiles (128 KB) + 32 KB scratch + the ring.
+#pragma once
+#include "infer_fused.cuh"
+
+namespace maz {
+namespace twin {
+
+using namespace umma;
+using fused::Desc;
+using fused::GH;
+using fused::GP;
+using fused::H;
+using fused::HD;
+using fused::NEPI;
+using fused::NTHREADS;
+using fused::PARTS;
+using fused::PH;
+using fused::PP;
+using fused::SUP;
+using fused::Thr;
+using fused::pack2;
+using fused::row_stats;
+using fused::store_cols;
+using fused::sum_sq;
+
+constexpr int NSLOT = 4;
+constexpr uint32_t SLOT_BYTES = 128 * 64 * 2;      // one K-half of a 128-row weight matrix
+constexpr uint32_t TILE_BYTES = 128 * 128 * 2;     // one bf16 operand tile
+constexpr uint32_t SCRATCH_BYTES = 32768;          // attention Q/K blocks (16 warps x 2 KB) | graph-head partials 24 KB + row statistics 4 KB
+constexpr uint32_t RED_OFF = 24576;
+constexpr uint32_t TM_TILE = 256, TM_A0 = 0, TM_A1 = 128;
+constexpr int NOPS = 29;                           // weight matrices = MMA groups per tile
+constexpr int NSTAGE = 25;
+
+__host__ __device__ inline size_t smem_bytes() { return 4 * (size_t)TILE_BYTES + SCRATCH_BYTES + NSLOT * (size_t)SLOT_BYTES + 1024; }
+
+// One MMA group: D[tile ACC `dst`] (+)= A[tile `asrc`: 0 = sX, 1 = sT] * W[mat]^T; `last` closes a stage.
+struct Op { unsigned char mat, asrc, dst, acc, last; };
+#define MAZ_TW_LAYER(b) {b, 0, 0, 0, 1}, {b + 1, 0, 0, 0, 0}, {b + 2, 0, 1, 0, 1}, {b + 3, 1, 0, 0, 1}, {b + 4, 0, 0, 0, 1}, {b + 5, 1, 0, 0, 1}
+__constant__ Op kOps[NOPS] = {
+    {0, 1, 0, 0, 1},                                       // in-proj on h
+    MAZ_TW_LAYER(1), MAZ_TW_LAYER(7), MAZ_TW_LAYER(13),    // per layer: V | Q, K | out-proj | linear1 | linear2
+    {19, 1, 0, 0, 0}, {20, 0, 0, 1, 1},                    // fc_dynamic.0 on [h | . | attention output]
+    {21, 1, 0, 0, 1}, {22, 0, 0, 0, 1},                    // fc_dynamic.3, fc_dynamic.6
+    {23, 1, 0, 0, 1}, {24, 0, 0, 0, 1},                    // reward graph net layer 1 (on h'), layer 2
+    {25, 1, 0, 0, 1}, {26, 0, 0, 0, 1},                    // value graph net
+    {27, 1, 0, 0, 1}, {28, 0, 0, 0, 1},                    // fc_policy.0, fc_policy.3
+};
+#undef MAZ_TW_LAYER
+__device__ __forceinline__ void mat_dims(int m, int NAP, uint32_t &n, uint32_t &k)
+{
+    n = 128; k = 128;
+    if (m == 24 || m == 26) k = GH;
+    else if (m == 27) n = PH;
+    else if (m == 28) { n = (uint32_t)NAP; k = PH; }
+}
+
+// ---- small helpers ---------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void add_gvec(float (&v)[NV], const float *__restrict__ p)
+{
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p + i));
+        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+    }
+}
+// v += the bf16 row segment [c, c + NV) of `row` in a K = 128 operand tile (the residual stream)
+template <int NV>
+__device__ __forceinline__ void add_xres(float (&v)[NV], uint32_t tile, int row, int c)
+{
+#pragma unroll
+    for (int j = 0; j < NV / 8; ++j) {
+        uint32_t w[4];
+        lds4u(tile + operand_chunk_off(row, (c >> 3) + j, H, 128), w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[8 * j + 2 * i] += __uint_as_float(w[i] << 16);
+            v[8 * j + 2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+}
+template <int NV>
+__device__ __forceinline__ void ln_affine_g(float (&v)[NV], float mean, float rstd, const float *__restrict__ pg, const float *__restrict__ pb)
+{
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(pg + i)), b = __ldg(reinterpret_cast<const float4 *>(pb + i));
+        v[i] = (v[i] - mean) * rstd * g.x + b.x; v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
+        v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z; v[i + 3] = (v[i + 3] - mean) * rstd * g.w + b.w;
+    }
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4])
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4])
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+
+// ---- epilogues (NOT inlined: small code, see infer_fused.cuh) -----------------------------------------------------------------
+// Thread layout as in infer_fused.cuh: 16 warps = 4 TMEM lane quadrants x 4 column parts; row = quad*32 + lane.
+// `trow`: TMEM address of the tile's ACC0 at this warp's lanes; `oh`: this row's column of the one-hot weight block (or NULL).
+
+// x0 = relu(acc + b_in + W_a[:, action]) + pos[agent] -> sX
+__device__ __noinline__ void epi_inproj(uint32_t trow, const float *__restrict__ pb, const float *__restrict__ oh, const float *__restrict__ pos,
+                                        uint32_t aX)
+{
+    const Thr t;
+    const int c = t.part * 32;
+    float v[32];
+    tmem_ld32(trow + TM_A0 + c, v);
+    add_gvec(v, pb + c);
+    if (oh) add_gvec(v, oh + c);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    add_gvec(v, pos + c);
+    store_cols(aX, t.row, c, H, v);
+}
+// acc + b -> bf16 tile (V of the attention; relu != 0: relu(linear1))
+__device__ __noinline__ void epi_bias(uint32_t trow, const float *__restrict__ pb, int relu, uint32_t tile)
+{
+    const Thr t;
+    const int c = t.part * 32;
+    float v[32];
+    tmem_ld32(trow + TM_A0 + c, v);
+    add_gvec(v, pb + c);
+    if (relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    store_cols(tile, t.row, c, H, v);
+}
+// y = LN(acc + b [+ oh] [+ x from res_tile]) * g + be, optional ReLU -> dst tile (bf16)
+__device__ __noinline__ void epi_ln(uint32_t trow, const float *__restrict__ pb, const float *__restrict__ pg, const float *__restrict__ pbe,
+                                    const float *__restrict__ oh, uint32_t res_tile, int relu_after, uint32_t dst_tile, uint32_t aRed)
+{
+    const Thr t;
+    const int c = t.part * 32;
+    float v[32];
+    tmem_ld32(trow + TM_A0 + c, v);
+    add_gvec(v, pb + c);
+    if (oh) add_gvec(v, oh + c);
+    if (res_tile) add_xres(v, res_tile, t.row, c);
+    float sum, sq;
+    sum_sq(v, sum, sq);
+    row_stats(t, aRed, sum, sq);
+    const float mean = sum * (1.f / H);
+    const float rstd = rsqrtf(fmaxf(sq * (1.f / H) - mean * mean, 0.f) + 1e-5f);
+    ln_affine_g(v, mean, rstd, pg + c, pbe + c);
+    if (relu_after) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    store_cols(dst_tile, t.row, c, H, v);
+}
+
+// Scaled dot-product attention over the agents of a root (attention.py:36-43 -> nn.MultiheadAttention, 8 heads x 16).
+// ACC0 = x Wq^T, ACC1 = x Wk^T (this stage), aT = bf16(x Wv^T + bv) (previous stage); the output replaces V in aT.
+// A warp (quad, part) owns token rows quad*32 .. +31 and heads 2*part, 2*part + 1; per head:
+//   Q (scaled by 1/sqrt(16), + bias) and K (+ bias) of the 32 rows -> two 32 x 16 bf16 blocks in the warp's scratch (core-matrix
+//   layout), S[32 x 32] = Q K^T on 8 MMAs, keys of other roots masked, row softmax on the fragments (a row's 32 scores sit in
+//   the 4 lanes of a quad), P as bf16 A fragments, O[32 x 16] = P V on 8 MMAs with V fragments by ldmatrix.trans from aT.
+// Rows beyond the last whole root of the warp form a pseudo-root of their own (finite garbage, never stored anywhere).
+__device__ __noinline__ void epi_attention(uint32_t trow, uint32_t aT, const float *__restrict__ pqk, int N, uint32_t scratch)
+{
+    const Thr t;
+    const int l = t.lane, m = l >> 3;
+    const uint32_t qb = scratch + (uint32_t)(t.part * 4 + t.quad) * 2048u, kb = qb + 1024u;
+    const uint32_t mine = (uint32_t)(l >> 3) * 256u + (uint32_t)(l & 7) * 16u;    // my row in a 32 x 16 block (k8 = 1: + 128)
+    int rs[2][2];                                                                    // first row of the root of my 4 fragment rows
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = mt * 16 + (l >> 2) + 8 * h;
+            rs[mt][h] = (r / N) * N;
+        }
+#pragma unroll 1
+    for (int hh = t.part * 2; hh < t.part * 2 + 2; ++hh) {
+        {
+            float q[16], k[16];
+            tmem_ld16(trow + TM_A0 + hh * HD, q);
+            tmem_ld16(trow + TM_A1 + hh * HD, k);
+            add_gvec(q, pqk + hh * HD);
+            add_gvec(k, pqk + H + hh * HD);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q[i] *= 0.25f;          // 1/sqrt(head_dim): a power of two, exact before the rounding
+            uint4 a;
+            a.x = pack2(q[0], q[1]); a.y = pack2(q[2], q[3]); a.z = pack2(q[4], q[5]); a.w = pack2(q[6], q[7]);
+            sts4(qb + mine, a);
+            a.x = pack2(q[8], q[9]); a.y = pack2(q[10], q[11]); a.z = pack2(q[12], q[13]); a.w = pack2(q[14], q[15]);
+            sts4(qb + mine + 128, a);
+            a.x = pack2(k[0], k[1]); a.y = pack2(k[2], k[3]); a.z = pack2(k[4], k[5]); a.w = pack2(k[6], k[7]);
+            sts4(kb + mine, a);
+            a.x = pack2(k[8], k[9]); a.y = pack2(k[10], k[11]); a.z = pack2(k[12], k[13]); a.w = pack2(k[14], k[15]);
+            sts4(kb + mine + 128, a);
+        }
+        __syncwarp();
+        float S[2][4][4];
+        {
+            uint32_t kf[2][4];                                   // B fragments of K: [key pair of 8-blocks][b0, b1 of block 2j | b0, b1 of block 2j+1]
+#pragma unroll
+            for (int j = 0; j < 2; ++j) ldsm_x4(kb + (uint32_t)(2 * j + (m >> 1)) * 256u + (uint32_t)(m & 1) * 128u + (uint32_t)(l & 7) * 16u, kf[j]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t a[4];
+                ldsm_x4(qb + (uint32_t)(2 * mt + (m & 1)) * 256u + (uint32_t)(m >> 1) * 128u + (uint32_t)(l & 7) * 16u, a);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.f;
+                    mma16816(S[mt][nt], a, kf[nt >> 1][(nt & 1) * 2], kf[nt >> 1][(nt & 1) * 2 + 1]);
+                }
+            }
+        }
+        float inv[2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = nt * 8 + 2 * (l & 3) + e;
+                        const float s = ((unsigned)(c - rs[mt][h]) < (unsigned)N) ? S[mt][nt][2 * h + e] : -INFINITY;
+                        S[mt][nt][2 * h + e] = s;
+                        mx = fmaxf(mx, s);
+                    }
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                float sum = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float p = __expf(S[mt][nt][2 * h + e] - mx);
+                        S[mt][nt][2 * h + e] = p;
+                        sum += p;
+                    }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                inv[mt][h] = 1.f / sum;
+            }
+        float O[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) O[mt][n2][0] = O[mt][n2][1] = O[mt][n2][2] = O[mt][n2][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t vf[4];                                      // V^T fragments: [b0, b1 of dims 0..7 | b0, b1 of dims 8..15] of keys ks*16 .. +15
+            ldsm_x4_t(aT + (uint32_t)(t.quad * 4 + ks * 2 + (m & 1)) * 2048u + (uint32_t)(hh * 2 + (m >> 1)) * 128u + (uint32_t)(l & 7) * 16u, vf);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t pa[4];
+                pa[0] = pack2(S[mt][2 * ks][0], S[mt][2 * ks][1]);
+                pa[1] = pack2(S[mt][2 * ks][2], S[mt][2 * ks][3]);
+                pa[2] = pack2(S[mt][2 * ks + 1][0], S[mt][2 * ks + 1][1]);
+                pa[3] = pack2(S[mt][2 * ks + 1][2], S[mt][2 * ks + 1][3]);
+                mma16816(O[mt][0], pa, vf[0], vf[1]);
+                mma16816(O[mt][1], pa, vf[2], vf[3]);
+            }
+        }
+        __syncwarp();                                            // every lane has its V fragments: the head's columns of aT may be overwritten
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row = t.quad * 32 + mt * 16 + (l >> 2) + 8 * h;
+                    sts32(aT + operand_chunk_off(row, hh * 2 + n2, H, 128) + (uint32_t)(l & 3) * 4u,
+                          pack2(O[mt][n2][2 * h] * inv[mt][h], O[mt][n2][2 * h + 1] * inv[mt][h]));
+                }
+        __syncwarp();                                            // Q / K blocks are free for the next head
+    }
+}
+
+// next_hidden = acc + b + hidden (fp32 residual straight from the pool); fp32 to global, bf16 to the tile
+__device__ __noinline__ void epi_next_hidden(uint32_t trow, const float *__restrict__ pb, const float *__restrict__ hrow, float *__restrict__ nh,
+                                             int valid, uint32_t tile)
+{
+    const Thr t;
+    const int c = t.part * 32;
+    float v[32];
+    tmem_ld32(trow + TM_A0 + c, v);
+    add_gvec(v, pb + c);
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 h = __ldcg(reinterpret_cast<const float4 *>(hrow + c + i));
+            v[i] += h.x; v[i + 1] += h.y; v[i + 2] += h.z; v[i + 3] += h.w;
+            *reinterpret_cast<float4 *>(nh + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+    }
+    store_cols(tile, t.row, c, H, v);
+}
+
+// v[i] <- sum of v[i] over the lanes [lo, lo + N) of my root.  Small teams: N broadcasts per value; larger ones: a segmented
+// inclusive scan (5 steps) + one broadcast from the root's last lane -- the shuffle crossbar moves one warp instruction per
+// clock and SM, and 16 x N shuffles per thread were ~14 k cycles per graph-net stage at N = 27.
+template <int NV>
+__device__ __forceinline__ void root_sum(float (&v)[NV], int lane, int lo, int N)
+{
+    if (N <= 6) {
+        float s[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s[i] = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) s[i] += __shfl_sync(0xffffffffu, v[i], lo + j);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = s[i];
+        return;
+    }
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const bool take = lane - dlt >= lo;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float u = __shfl_up_sync(0xffffffffu, v[i], dlt);
+            if (take) v[i] += u;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __shfl_sync(0xffffffffu, v[i], lo + N - 1);
+}
+
+// GraphNetNN layer (model.py:151-163) from one stacked GEMM: columns [0,64) = gc.lin(x), [64,128) = nn(x).
+// y = LN(relu(sum_over_agents(gc + b_gc) + nn + b_nn)), no affine.  pb: [b_gc | b_nn | (head: V weights 11 x 64 | V bias)].
+// head == 0: y (bf16) -> `tile` (K = 64 layout).
+// head == 1: mean-pool over the agents, 64 -> 11 head, support transform.  The head is linear, so every thread first reduces ITS
+//            16 features of ITS row to 11 partial logits; the four column parts of a row are combined through shared memory,
+//            the rows of a root by the part-0 warp (root_sum over 11 values instead of 16 features x 4 parts).  The scalar is
+//            returned by the part-0 thread of every row.
+__device__ __noinline__ float epi_gnn(uint32_t trow, const float *__restrict__ pb, const float *__restrict__ oh, int N, int root_lane0, int head,
+                                      uint32_t tile, uint32_t aRed, uint32_t scratch)
+{
+    const Thr t;
+    const int c = t.part * GP;
+    float y[GP], nn[GP];
+    tmem_ld16(trow + TM_A0 + c, y);
+    add_gvec(y, pb + c);
+    if (oh) add_gvec(y, oh + c);
+    root_sum(y, t.lane, root_lane0, N);
+    tmem_ld16(trow + TM_A0 + GH + c, nn);
+    add_gvec(nn, pb + GH + c);
+    if (oh) add_gvec(nn, oh + GH + c);
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < GP; ++i) {
+        y[i] = fmaxf(y[i] + nn[i], 0.f);
+        sum += y[i];
+        sq += y[i] * y[i];
+    }
+    row_stats(t, aRed, sum, sq);
+    const float mean = sum * (1.f / GH);
+    const float rstd = rsqrtf(fmaxf(sq * (1.f / GH) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < GP; ++i) y[i] = (y[i] - mean) * rstd;
+    if (!head) {
+        store_cols(tile, t.row, c, GH, y);
+        return 0.f;
+    }
+    const float *pV = pb + 2 * GH, *pVb = pV + SUP * GH;
+    float lg[12];
+    lg[11] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SUP; ++k) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < GP; i += 4) {
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(pV + k * GH + c + i));
+            a += w.x * y[i] + w.y * y[i + 1] + w.z * y[i + 2] + w.w * y[i + 3];
+        }
+        lg[k] = a;
+    }
+    const uint32_t mine_out = scratch + (uint32_t)((t.row * PARTS + t.part) * 12) * 4u;
+#pragma unroll
+    for (int k = 0; k < 12; k += 4) sts4(mine_out + 4 * k, make_uint4(__float_as_uint(lg[k]), __float_as_uint(lg[k + 1]), __float_as_uint(lg[k + 2]), __float_as_uint(lg[k + 3])));
+    named_bar_sync(1 + t.quad, 128);
+    float out = 0.f;
+    if (t.part == 0) {                               // warp-uniform
+        const uint32_t rowp = scratch + (uint32_t)(t.row * PARTS * 12) * 4u;
+#pragma unroll
+        for (int p = 1; p < PARTS; ++p)
+#pragma unroll
+            for (int k = 0; k < 12; k += 4) {
+                uint32_t w0, w1, w2, w3;
+                lds4u(rowp + (uint32_t)(p * 12 + k) * 4u, w0, w1, w2, w3);
+                lg[k] += __uint_as_float(w0); lg[k + 1] += __uint_as_float(w1); lg[k + 2] += __uint_as_float(w2); lg[k + 3] += __uint_as_float(w3);
+            }
+        root_sum(lg, t.lane, root_lane0, N);
+        const float invn = 1.f / (float)N;
+        float l11[SUP];
+#pragma unroll
+        for (int k = 0; k < SUP; ++k) l11[k] = lg[k] * invn + __ldg(pVb + k);
+        out = fused::support_to_scalar(l11);
+    }
+    named_bar_sync(1 + t.quad, 128);                 // the partials are consumed: the other tile's call may overwrite them
+    return out;
+}
+
+// policy hidden: p1 = relu(LN(acc + b) * g + be) over 32 columns -> operand tile (K = 32)
+__device__ __noinline__ void epi_policy_hidden(uint32_t trow, const float *__restrict__ pp, uint32_t tile, uint32_t aRed)
+{
+    const Thr t;
+    const int c = t.part * PP;
+    float p[PP];
+    tmem_ld8(trow + TM_A0 + c, p);
+    add_gvec(p, pp + c);
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < PP; ++i) { sum += p[i]; sq += p[i] * p[i]; }
+    row_stats(t, aRed, sum, sq);
+    const float mean = sum * (1.f / PH);
+    const float rstd = rsqrtf(fmaxf(sq * (1.f / PH) - mean * mean, 0.f) + 1e-5f);
+    ln_affine_g(p, mean, rstd, pp + PH + c, pp + 2 * PH + c);
+#pragma unroll
+    for (int i = 0; i < PP; ++i) p[i] = fmaxf(p[i], 0.f);
+    store_cols(tile, t.row, c, PH, p);
+}
+
+// policy logits -> softmax -> probs, beta = probs^(1/tau) renormalised (mcts_sampled.py:158-161), greedy action.
+// Column part p owns logits [16p, 16p + 16) of its row (parts beyond the padded action count idle); row maximum / argmax and the
+// two sums are combined across the parts of a row through shared memory (ex1, ex2: 4 KB each).
+__device__ __noinline__ void epi_policy_out(const Desc &d, uint32_t trow, const float *__restrict__ pb2, int valid, int root, int agent,
+                                            uint32_t ex1, uint32_t ex2)
+{
+    const Thr t;
+    const int A = d.A, cc = t.part * 16;
+    const bool active = cc < d.NAP;                  // warp-uniform (tcgen05.ld is warp-collective)
+    float v[16];
+    float m = -INFINITY;
+    int am = 0;
+    if (active) {
+        tmem_ld16(trow + TM_A0 + cc, v);
+        add_gvec(v, pb2 + cc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (cc + i < A && v[i] > m) { m = v[i]; am = cc + i; }
+        if (valid && d.logits_out) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (cc + i < A) d.logits_out[((size_t)root * d.N + agent) * A + cc + i] = v[i];
+        }
+    }
+    sts2f(ex1 + (uint32_t)(t.row * PARTS + t.part) * 8u, m, __int_as_float(am));
+    named_bar_sync(1 + t.quad, 128);
+    m = -INFINITY;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) {                // first maximum in column order, as torch.argmax
+        const float2 o = lds2f(ex1 + (uint32_t)(t.row * PARTS + p) * 8u);
+        if (o.x > m) { m = o.x; am = __float_as_int(o.y); }
+    }
+    const bool unit_tau = (d.inv_tau == 1.0f);
+    float s = 0.f, sbeta = 0.f;
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float e = (cc + i < A) ? __expf(v[i] - m) : 0.f;
+            v[i] = e;
+            s += e;
+            sbeta += unit_tau ? e : ((cc + i < A) ? __powf(e, d.inv_tau) : 0.f);   // (e/s)^t = e^t / s^t
+        }
+    }
+    sts2f(ex2 + (uint32_t)(t.row * PARTS + t.part) * 8u, s, sbeta);
+    named_bar_sync(1 + t.quad, 128);
+    s = 0.f; sbeta = 0.f;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) {
+        const float2 o = lds2f(ex2 + (uint32_t)(t.row * PARTS + p) * 8u);
+        s += o.x; sbeta += o.y;
+    }
+    if (t.part == 0 && valid && d.greedy) d.greedy[(size_t)root * d.N + agent] = am;
+    const int ta = (d.cur < 0) ? agent : (agent == d.cur ? 0 : -1);
+    if (active && valid && ta >= 0) {
+        const float invs = 1.f / s, invb = 1.f / sbeta;
+        float *po = d.probs + ((size_t)root * d.Nt + ta) * A, *bo = d.beta + ((size_t)root * d.Nt + ta) * A;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (cc + i < A) {
+                po[cc + i] = v[i] * invs;
+                bo[cc + i] = (unit_tau ? v[i] : __powf(v[i], d.inv_tau)) * invb;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const __grid_constant__ Desc d)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_mma[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int N = d.N;
+    uint8_t *s0 = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    const uint32_t aTile = smem_u32(s0);                         // tile tt: sX at aTile + tt*2*TILE_BYTES, sT right after it
+    const uint32_t aScr = aTile + 4 * TILE_BYTES, aRed = aScr + RED_OFF;
+    uint8_t *sW = s0 + 4 * TILE_BYTES + SCRATCH_BYTES;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == NEPI / 32) {
+        // ================================ weight producer: stage-major, each stage's pieces once per tile ==================
+        if ((tid & 31) == 0) {
+            int pc = 0;
+#pragma unroll 1
+            for (int i = 0; i < NOPS;) {
+                int j = i;
+                while (!kOps[j].last) ++j;
+#pragma unroll 1
+                for (int tt = 0; tt < 2; ++tt)
+#pragma unroll 1
+                    for (int o = i; o <= j; ++o) {
+                        const int mat = kOps[o].mat;
+                        uint32_t n, k;
+                        mat_dims(mat, d.NAP, n, k);
+                        const uint8_t *src = reinterpret_cast<const uint8_t *>(d.wpk) + d.chunk_off[mat];
+#pragma unroll 1
+                        for (uint32_t k0 = 0; k0 < k; k0 += 64, ++pc) {
+                            const uint32_t kk = min(64u, k - k0), bytes = n * kk * 2u;
+                            const int s = pc % NSLOT;
+                            if (pc >= NSLOT) mbar_wait_backoff(&bar_empty[s], ((pc / NSLOT) - 1) & 1);
+                            mbar_expect_tx(&bar_full[s], bytes);
+                            bulk_g2s(sW + (size_t)s * SLOT_BYTES, src, bytes, &bar_full[s]);
+                            src += bytes;
+                        }
+                    }
+                i = j + 1;
+            }
+        }
+    } else if (warp == NEPI / 32 + 1) {
+        // ================================ MMA issuer ==========================================================================
+        const bool issuer = (tid & 31) == 0;
+        const uint32_t aW = smem_u32(sW);
+        int pc = 0;
+#pragma unroll 1
+        for (int i = 0; i < NOPS;) {
+            int j = i;
+            while (!kOps[j].last) ++j;
+#pragma unroll 1
+            for (int tt = 0; tt < 2; ++tt) {
+                named_bar_sync(5, NEPI + 32);                    // tile tt's operands for this stage are published
+                tc_fence_after();
+                if (issuer) {
+#pragma unroll 1
+                    for (int o = i; o <= j; ++o) {
+                        const Op op = kOps[o];
+                        uint32_t n, k;
+                        mat_dims(op.mat, d.NAP, n, k);
+                        const uint32_t a_addr = aTile + (uint32_t)tt * 2u * TILE_BYTES + (op.asrc ? TILE_BYTES : 0u);
+                        const uint32_t dst = tmem + (uint32_t)tt * TM_TILE + (op.dst ? TM_A1 : TM_A0);
+#pragma unroll 1
+                        for (uint32_t k0 = 0; k0 < k; k0 += 64, ++pc) {
+                            const uint32_t kk = min(64u, k - k0);
+                            const int s = pc % NSLOT;
+                            mbar_wait(&bar_full[s], (pc / NSLOT) & 1);
+                            tc_fence_after();
+                            issue_gemm(dst, a_addr, k, k0, aW + (uint32_t)s * SLOT_BYTES, kk, 0, kk, n, op.acc != 0 || k0 != 0);
+                            mma_commit(&bar_empty[s]);           // the slot is free once these MMAs have read it
+                        }
+                    }
+                    mma_commit(&bar_mma[tt]);
+                }
+                __syncwarp();
+            }
+            i = j + 1;
+        }
+    } else {
+        // ================================ epilogue warps ======================================================================
+        const Thr t;
+        const float *__restrict__ P = d.vec;
+        const int rpw = 32 / N;
+        const int rl = t.lane / N, agent = t.lane - rl * N;
+        const int root_lane0 = (rl < rpw) ? rl * N : 0;
+        const int root0 = ((blockIdx.x * 2) * 4 + t.quad) * rpw + rl;          // tile tt: + tt * 4 * rpw
+        const int valid0 = (rl < rpw) && (root0 < d.B), valid1 = (rl < rpw) && (root0 + 4 * rpw < d.B);
+        const uint32_t trow0 = tmem + ((uint32_t)(t.quad * 32) << 16);
+        uint32_t ph = 0;
+        int ts_n = 0;
+        const bool ts_on = d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0;
+#define TS() \
+    if (ts_on && ts_n < 256) d.dbg_clock[ts_n++] = clock64();
+#define TILE_VARS                                                         \
+    const uint32_t trow = trow0 + (uint32_t)tt * TM_TILE;                 \
+    const uint32_t aX = aTile + (uint32_t)tt * 2u * TILE_BYTES, aT = aX + TILE_BYTES; \
+    const int valid = tt ? valid1 : valid0;                               \
+    const int root = root0 + tt * 4 * rpw;                                \
+    const float *hrow = tt ? hrow1 : hrow0;                               \
+    const int act = tt ? act1 : act0;                                     \
+    (void)trow, (void)aX, (void)aT, (void)valid, (void)root, (void)hrow, (void)act;
+#define WAIT_MMA()                                 \
+    mbar_wait(&bar_mma[tt], (ph >> tt) & 1u);      \
+    ph ^= 1u << tt;                                \
+    tc_fence_after();                              \
+    TS();
+#define PUBLISH()                      \
+    TS();                              \
+    fence_proxy_async();               \
+    tc_fence_before();                 \
+    named_bar_sync(5, NEPI + 32);
+#define STAGE(body)                            \
+    _Pragma("unroll 1") for (int tt = 0; tt < 2; ++tt) { \
+        TILE_VARS                              \
+        WAIT_MMA();                            \
+        body;                                  \
+        PUBLISH();                             \
+    }
+
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        // ---- per tile: the parent's hidden-state row and my agent's action ------------------------------------------------
+        const float *hrow0 = d.pool, *hrow1 = d.pool;
+        int act0 = -1, act1 = -1;
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+            const int valid = tt ? valid1 : valid0, root = root0 + tt * 4 * rpw;
+            const float *hr = d.pool;
+            int a = -1;
+            if (valid) {
+                const int ix = d.idx_x ? __ldcg(d.idx_x + root) : 0;
+                hr = d.pool + ((size_t)ix * d.B + root) * (size_t)(N * H) + (size_t)agent * H;
+                if (d.greedy_pool == nullptr || d.cur < 0)
+                    a = __ldcg(d.actions + (size_t)root * N + agent);
+                else if (agent == d.cur)                      // sequential-agent mode, joint action assembled here (mcts_sampled.py:116-147)
+                    a = __ldcg(d.actions + root);
+                else if (agent < d.cur)
+                    a = d.factor ? __ldcg(d.factor + (size_t)root * N + agent) : 0;
+                else
+                    a = __ldcg(d.greedy_pool + ((size_t)ix * d.B + root) * N + agent);
+                if (a < 0 || a >= d.A) a = -1;
+            }
+            if (tt) { hrow1 = hr; act1 = a; } else { hrow0 = hr; act0 = a; }
+        }
+        TS();
+#pragma unroll 1
+        for (int tt = 0; tt < 2; ++tt) {
+            TILE_VARS
+            fused::gather_hidden(hrow, valid, aT);
+            PUBLISH();
+        }
+        // ---- attention_stack[0..1]: x0 = relu(W_in [h | onehot] + b) + positional table ------------------------------------
+        STAGE(epi_inproj(trow, P + d.o_bin, act >= 0 ? P + d.o_oh_in + act * H : nullptr, P + d.o_pos + agent * H, aX));
+        // ---- 3 x post-LN TransformerEncoderLayer over the agent axis (attention.py:36-43) ----------------------------------
+#pragma unroll 1
+        for (int l = 0; l < 3; ++l) {
+            const float *lv = P + d.o_layer + l * 1280;   // bq bk bv bo g1 be1 b1 b2 g2 be2
+            STAGE(epi_bias(trow, lv + 256, 0, aT));                                                   // V
+            STAGE(epi_attention(trow, aT, lv, N, aScr));                                              // Q | K -> attention
+            STAGE(epi_ln(trow, lv + 384, lv + 512, lv + 640, nullptr, aX, 0, aX, aRed));              // norm1(x + out_proj)
+            STAGE(epi_bias(trow, lv + 768, 1, aT));                                                   // relu(linear1)
+            STAGE(epi_ln(trow, lv + 896, lv + 1024, lv + 1152, nullptr, aX, 0, aX, aRed);             // norm2(x + linear2)
+                  if (l == 2) fused::gather_hidden(hrow, valid, aT));                                 // h (bf16) back for fc_dynamic
+        }
+        // ---- fc_dynamic: Linear-LN-ReLU, Linear-LN-ReLU, Linear; residual (model.py:262-268) --------------------------------
+        const float *dv = P + d.o_dyn;
+        STAGE(epi_ln(trow, dv, dv + 128, dv + 256, act >= 0 ? P + d.o_oh_dyn + act * H : nullptr, 0, 1, aT, aRed));
+        STAGE(epi_ln(trow, dv + 384, dv + 512, dv + 640, nullptr, 0, 1, aX, aRed));
+        STAGE(epi_next_hidden(trow, dv + 768, hrow, d.next_hidden + (valid ? (size_t)root * (N * H) + (size_t)agent * H : 0), valid, aT));
+        // ---- reward head: GraphNetNN on [next_hidden | onehot] (model.py:270-277) -------------------------------------------
+        const float *rv = P + d.o_rg;
+        STAGE(epi_gnn(trow, rv, act >= 0 ? P + d.o_oh_rg + act * H : nullptr, N, root_lane0, 0, aX, aRed, aScr));
+        STAGE({
+            const float r = epi_gnn(trow, rv + 128, nullptr, N, root_lane0, 1, 0, aRed, aScr);
+            if (valid && agent == 0 && t.part == 0) d.reward[root] = r;
+        });
+        // ---- value head: GraphNetNN on next_hidden (model.py:359) -------------------------------------------------------------
+        const float *vv = P + d.o_vg;
+        STAGE(epi_gnn(trow, vv, nullptr, N, root_lane0, 0, aX, aRed, aScr));
+        STAGE({
+            const float val = epi_gnn(trow, vv + 128, nullptr, N, root_lane0, 1, 0, aRed, aScr);
+            if (valid && agent == 0 && t.part == 0) d.value[root] = val;
+        });
+        // ---- policy head + the driver's softmax / beta ---------------------------------------------------------------------------
+        const float *pv = P + d.o_pol;
+        STAGE(epi_policy_hidden(trow, pv, aX, aRed));
+#pragma unroll 1
+        for (int tt = 0; tt < 2; ++tt) {
+            TILE_VARS
+            WAIT_MMA();
+            epi_policy_out(d, trow, pv + 96, valid, root, agent, aRed, aScr);
+            named_bar_sync(1 + t.quad, 128);        // (the other tile's call reuses the exchange buffers)
+            TS();
+        }
+#undef STAGE
+#undef PUBLISH
+#undef WAIT_MMA
+#undef TILE_VARS
+#undef TS
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace twin
+}  // namespace maz

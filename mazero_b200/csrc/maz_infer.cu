@@ -8,6 +8,7 @@
 #include "umma.cuh"
 #include "infer_fused.cuh"
 #include "infer_hmma.cuh"
+#include "infer_twin.cuh"
 
 using namespace maz;
 using namespace maz::umma;
@@ -101,11 +102,16 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
     if (!d->pool || !d->actions || !d->next_hidden || !d->reward || !d->value || !d->probs || !d->beta || !d->wpk || !d->vec)
         return set_last_error(1, "maz_infer_recurrent: NULL tensor");
     if (d->vec_floats <= 0 || d->vec_floats % 4) return set_last_error(1, "maz_infer_recurrent: vec_floats must be a positive multiple of 4");
-    const size_t dyn = fused::smem_bytes(d->KA, d->vec_floats);
+    const bool tw = d->tc_layout == 1;
+    if (d->tc_layout != 0 && !tw) return set_last_error(1, "maz_infer_recurrent: unknown tc_layout");
+    if (tw && (d->o_oh_in <= 0 || d->o_oh_dyn <= 0 || d->o_oh_rg <= 0 || d->o_oh_rg + d->A * 128 > d->vec_floats))
+        return set_last_error(1, "maz_infer_recurrent: tc_layout 1 needs the one-hot weight tables behind vec");
+    const size_t dyn = tw ? twin::smem_bytes() : fused::smem_bytes(d->KA, d->vec_floats);
     if (dyn > 227 * 1024) return set_last_error(3, "maz_infer_recurrent: parameters do not fit in shared memory");
     if (int rc = maz_infer_configure(d->vec_floats, d->KA)) return rc;
     const int roots_per_tile = 4 * (32 / d->N);
-    const int tiles = (d->B + roots_per_tile - 1) / roots_per_tile;
+    int tiles = (d->B + roots_per_tile - 1) / roots_per_tile;
+    if (tw) tiles = (tiles + 1) / 2;                      // a CTA of the second-generation kernel owns two tiles
     // programmatic dependent of the tree kernel: TMEM allocation, barrier set-up and the weight / parameter
     // streaming overlap the predecessor's tail; the epilogue warps call griddepcontrol.wait before they read it
     cudaLaunchConfig_t cfg = {};
@@ -118,7 +124,7 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (maz::pdl_mask() & 1) ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fused::k_recurrent_inference, *d);
+    cudaError_t e = tw ? cudaLaunchKernelEx(&cfg, twin::k_recurrent_inference_twin, *d) : cudaLaunchKernelEx(&cfg, fused::k_recurrent_inference, *d);
     if (e != cudaSuccess) return set_last_error(2, std::string("k_recurrent_inference: ") + cudaGetErrorString(e));
     return 0;
 }
@@ -146,6 +152,9 @@ extern "C" int maz_infer_configure(int vec_floats, int ka)
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fused::k_recurrent_inference);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(fused::k_recurrent_inference, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, twin::k_recurrent_inference_twin);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(twin::k_recurrent_inference_twin, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return set_last_error(2, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     done[dev] = true;
     return 0;

@@ -26,6 +26,7 @@ class InferDesc(C.Structure):
         ("o_bin", C.c_int), ("o_pos", C.c_int), ("o_layer", C.c_int), ("o_dyn", C.c_int), ("o_rg", C.c_int),
         ("o_vg", C.c_int), ("o_pol", C.c_int), ("dbg_clock", C.c_void_p), ("dbg_flags", C.c_int),
         ("roots_per_tile", C.c_int), ("factor", C.c_void_p), ("greedy_pool", C.c_void_p),
+        ("tc_layout", C.c_int), ("o_oh_in", C.c_int), ("o_oh_dyn", C.c_int), ("o_oh_rg", C.c_int),
     ]
 
 
@@ -160,6 +161,31 @@ class FusedParams:
         self.chunk_off = offs
         self.chunk_bytes = [t.numel() * 2 for t in packed]
 
+        # two-tiles-in-flight kernel (csrc/infer_twin.cuh): 29 matrices in the order of its stage table (per layer V, Q, K,
+        # out-proj, linear1, linear2; no one-hot blocks), each stored as K-halves (pieces of <= 64 input features, <= 16 KB)
+        tw = [c[0]]
+        for l in range(3):
+            b = 2 + 6 * l
+            tw += [c[b + 2], c[b], c[b + 1], c[b + 3], c[b + 4], c[b + 5]]
+        tw += [c[20], c[22], c[23], c[24], c[25], c[27], c[28], c[29], c[30], c[31]]
+        assert len(tw) == 29
+        tp = []
+        for m in tw:
+            m = m.contiguous()
+            tp.append(torch.cat([pack_operand(m[:, k0:k0 + 64].contiguous()) for k0 in range(0, m.shape[1], 64)]))
+        offs_t, o = [], 0
+        for t in tp:
+            offs_t.append(o)
+            o += t.numel() * 2
+        wpk_t = torch.cat(tp)
+        self.chunk_off_t, self.chunk_bytes_t = offs_t + [0] * (NCHUNK - 29), [t.numel() * 2 for t in tp] + [0] * (NCHUNK - 29)
+        if getattr(self, "wpk_t", None) is None:
+            self.wpk_t = wpk_t
+        else:
+            self.wpk_t.copy_(wpk_t)
+        # the one-hot blocks as fp32 [A][128] tables of the bf16-rounded weights (what the one-hot MMA would have added)
+        oh = [w[:, H:H + A].to(torch.bfloat16).to(torch.float32).t().contiguous() for w in (w_in, wd1, wr1)]
+
         vec, self.off = [], {}
 
         def put(name, *ts):
@@ -188,14 +214,18 @@ class FusedParams:
             vecf = torch.cat([vecf, torch.zeros(4 - vecf.numel() % 4, device=dev)])
         vecf = vecf.contiguous()
         assert all(o % 4 == 0 for o in self.off.values())
+        self.off_oh = [vecf.numel() + i * A * H for i in range(3)]
+        vec_t = torch.cat([vecf] + [t.reshape(-1) for t in oh]).contiguous()
         if self.wpk is None:
-            self.wpk, self.vec = wpk, vecf
+            self.wpk, self.vec, self.vec_t = wpk, vecf, vec_t
         else:                      # keep addresses stable for captured CUDA graphs
             self.wpk.copy_(wpk)
             self.vec.copy_(vecf)
+            self.vec_t.copy_(vec_t)
 
     def desc(self, B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy=None, logits_out=None,
-             tree_agents=None, cur=-1, inv_tau=1.0, dbg_clock=None, small=False, factor=None, greedy_pool=None, roots_per_tile=0):
+             tree_agents=None, cur=-1, inv_tau=1.0, dbg_clock=None, small=False, factor=None, greedy_pool=None, roots_per_tile=0,
+             twin=None):
         ptr = lambda t: (t.data_ptr() if t is not None else None)
         dsc = InferDesc()
         dsc.B, dsc.N, dsc.A, dsc.KA, dsc.NAP = int(B), self.N, self.A, self.KA, self.KA
@@ -208,8 +238,14 @@ class FusedParams:
         dsc.factor, dsc.greedy_pool, dsc.roots_per_tile = ptr(factor), ptr(greedy_pool), int(roots_per_tile)
         import os as _os
         dsc.dbg_flags = int(_os.environ.get('MAZ_DBG_FLAGS', '0'))
+        twin = (not small) and (use_twin() if twin is None else bool(twin))
         dsc.wpk, dsc.vec, dsc.vec_floats = (self.wpk_h if small else self.wpk).data_ptr(), self.vec.data_ptr(), self.vec.numel()
         co, cb = (self.chunk_off_h, self.chunk_bytes_h) if small else (self.chunk_off, self.chunk_bytes)
+        if twin:
+            dsc.tc_layout = 1
+            dsc.wpk, dsc.vec, dsc.vec_floats = self.wpk_t.data_ptr(), self.vec_t.data_ptr(), self.vec_t.numel()
+            co, cb = self.chunk_off_t, self.chunk_bytes_t
+            dsc.o_oh_in, dsc.o_oh_dyn, dsc.o_oh_rg = self.off_oh
         for i in range(NCHUNK):
             dsc.chunk_off[i], dsc.chunk_bytes[i] = co[i], cb[i]
         o = self.off
@@ -230,6 +266,11 @@ FusedParams.weights_desc = _weights_desc
 # (a CTA per floor(32/N) roots) but re-reads the 0.9 MB of weights from L2 once per CTA.  MAZ_INFER_KERNEL=small|tcgen05
 # forces one; "auto" takes the small-batch kernel while its grid stays within SMALL_MAX_TILES.
 SMALL_MAX_TILES = int(os.environ.get("MAZ_INFER_SMALL_MAX_TILES", "222"))   # 1.5 waves of 148 SMs (measured cross-over, profiles/prof_infer_cmp.py)
+
+
+def use_twin():
+    """Large-batch kernel generation: two tiles in flight per CTA (csrc/infer_twin.cuh) unless MAZ_INFER_TC=v1."""
+    return os.environ.get("MAZ_INFER_TC", "twin") != "v1"
 
 
 def use_small(B, N):

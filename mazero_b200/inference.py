@@ -148,8 +148,9 @@ class SmacInference:
         from . import fused
 
         small = fused.use_small(int(B), self.N) if kernel is None else (kernel == "small")
+        twin = None if kernel is None else (kernel == "twin")       # "tcgen05": first-generation one-tile-per-CTA kernel
         dsc = self.fused.desc(B, pool, idx_x, actions, next_hidden, reward, value, probs, beta, greedy, logits_out,
-                              tree_agents, cur, inv_tau, dbg_clock, small=small)
+                              tree_agents, cur, inv_tau, dbg_clock, small=small, twin=twin)
         fused.launch(dsc, (stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream, small)
 
     # ---- pieces ----------------------------------------------------------------------------------------

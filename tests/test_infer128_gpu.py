@@ -46,7 +46,7 @@ def test_fp32_parity_mode_matches_reference_network(built_lib, path):
         assert e <= tol, f"{key}: {e} > {tol}"
 
 
-@pytest.mark.parametrize("kernel", ["tcgen05", "small"])
+@pytest.mark.parametrize("kernel", ["twin", "tcgen05", "small"])
 @pytest.mark.parametrize("path", GOLDEN128, ids=IDS128)
 def test_fused_kernels_match_reference_network(built_lib, path, kernel):
     """prediction (a16: greedy actions / policy of the expanded node) and recurrent_inference (a17), two chained steps."""

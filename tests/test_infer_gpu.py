@@ -29,7 +29,7 @@ def test_umma_gemm_stage(built_lib, n, k):
     assert err < 2e-3, f"max abs err {err}"     # fp32 accumulation-order noise only
 
 
-@pytest.mark.parametrize("kernel", ["tcgen05", "small"])
+@pytest.mark.parametrize("kernel", ["twin", "tcgen05", "small"])
 @pytest.mark.parametrize("N,A,B", [(3, 9, 100), (5, 11, 70), (10, 18, 33), (27, 36, 9), (1, 5, 130), (2, 3, 16), (2, 40, 20),
                                    (30, 17, 5), (3, 9, 1)])
 def test_fused_recurrent_inference_matches_fp32_reference(built_lib, N, A, B, kernel):
