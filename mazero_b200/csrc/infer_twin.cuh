@@ -21,8 +21,8 @@
 //     whatever the team size (the scalar loop was ~110 instructions per key, head and row).
 //   * The one-hot joint-action operand is gone: `W [h | onehot(a)]` = `W_h h + W_a[:, a]`, the column is added in the epilogue
 //     from an fp32 table (three fewer MMA groups, no one-hot tiles in shared memory).
-//   * Weights stream through a 4 x 16 KB ring in K-halves (a 128 x 128 matrix is two pieces); slots are released by
-//     tcgen05.commit from the MMA warp.  Biases / LayerNorm affines / heads are read from global memory (L1-resident):
+//   * Weights stream through a 4 x 16 KB ring in K-halves (a 128 x 128 matrix is two pieces), ONCE per CTA: a stage's pieces
+//     (at most 4) serve tile A and then tile B and are released by tcgen05.commit after tile B's MMAs.  Biases / LayerNorm affines / heads are read from global memory (L1-resident):
 //     shared memory holds 4 operand tiles (128 KB) + 32 KB scratch + the ring.
 #pragma once
 #include "infer_fused.cuh"
@@ -90,6 +90,31 @@ __device__ __forceinline__ void add_gvec(float (&v)[NV], const float *__restrict
         v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
     }
 }
+// 256-bit global accesses (sm_100): a thread that owns a row segment moves whole 32-byte sectors per instruction.  The LSU
+// takes about one sector per clock and SM, and a row-per-thread access touches 32 different sectors per warp instruction:
+// with 128-bit accesses every sector was requested twice (next_hidden, the gathers: ~12 k cycles per tile at 27m).
+__device__ __forceinline__ void ldg256(const float *p, float (&v)[8])
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float *p, const float (&v)[8])
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+                 "f"(v[6]), "f"(v[7]) : "memory");
+}
+// v += a per-row vector in global memory (one-hot weight column), 32-byte aligned
+template <int NV>
+__device__ __forceinline__ void add_grow(float (&v)[NV], const float *__restrict__ p)
+{
+#pragma unroll
+    for (int i = 0; i < NV; i += 8) {
+        float t[8];
+        ldg256(p + i, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i + j] += t[j];
+    }
+}
 // v += the bf16 row segment [c, c + NV) of `row` in a K = 128 operand tile (the residual stream)
 template <int NV>
 __device__ __forceinline__ void add_xres(float (&v)[NV], uint32_t tile, int row, int c)
@@ -144,10 +169,10 @@ __device__ __noinline__ void epi_inproj(uint32_t trow, const float *__restrict__
     float v[32];
     tmem_ld32(trow + TM_A0 + c, v);
     add_gvec(v, pb + c);
-    if (oh) add_gvec(v, oh + c);
+    if (oh) add_grow(v, oh + c);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-    add_gvec(v, pos + c);
+    add_grow(v, pos + c);
     store_cols(aX, t.row, c, H, v);
 }
 // acc + b -> bf16 tile (V of the attention; relu != 0: relu(linear1))
@@ -173,7 +198,7 @@ __device__ __noinline__ void epi_ln(uint32_t trow, const float *__restrict__ pb,
     float v[32];
     tmem_ld32(trow + TM_A0 + c, v);
     add_gvec(v, pb + c);
-    if (oh) add_gvec(v, oh + c);
+    if (oh) add_grow(v, oh + c);
     if (res_tile) add_xres(v, res_tile, t.row, c);
     float sum, sq;
     sum_sq(v, sum, sq);
@@ -321,13 +346,26 @@ __device__ __noinline__ void epi_next_hidden(uint32_t trow, const float *__restr
     tmem_ld32(trow + TM_A0 + c, v);
     add_gvec(v, pb + c);
     if (valid) {
+        add_grow(v, hrow + c);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            const float4 h = __ldcg(reinterpret_cast<const float4 *>(hrow + c + i));
-            v[i] += h.x; v[i + 1] += h.y; v[i + 2] += h.z; v[i + 3] += h.w;
-            *reinterpret_cast<float4 *>(nh + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 32; i += 8) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = v[i + j];
+            stg256(nh + c + i, o);
         }
     }
+    store_cols(tile, t.row, c, H, v);
+}
+// fp32 pool row -> bf16 operand tile (K = 128), my 32 columns
+__device__ __noinline__ void gather_hidden(const float *__restrict__ hrow, int valid, uint32_t tile)
+{
+    const Thr t;
+    const int c = t.part * 32;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    if (valid) add_grow(v, hrow + c);
     store_cols(tile, t.row, c, H, v);
 }
 
@@ -378,11 +416,11 @@ __device__ __noinline__ float epi_gnn(uint32_t trow, const float *__restrict__ p
     float y[GP], nn[GP];
     tmem_ld16(trow + TM_A0 + c, y);
     add_gvec(y, pb + c);
-    if (oh) add_gvec(y, oh + c);
+    if (oh) add_grow(y, oh + c);
     root_sum(y, t.lane, root_lane0, N);
     tmem_ld16(trow + TM_A0 + GH + c, nn);
     add_gvec(nn, pb + GH + c);
-    if (oh) add_gvec(nn, oh + GH + c);
+    if (oh) add_grow(nn, oh + GH + c);
     float sum = 0.f, sq = 0.f;
 #pragma unroll
     for (int i = 0; i < GP; ++i) {
@@ -462,7 +500,7 @@ __device__ __noinline__ void epi_policy_hidden(uint32_t trow, const float *__res
 // Column part p owns logits [16p, 16p + 16) of its row (parts beyond the padded action count idle); row maximum / argmax and the
 // two sums are combined across the parts of a row through shared memory (ex1, ex2: 4 KB each).
 __device__ __noinline__ void epi_policy_out(const Desc &d, uint32_t trow, const float *__restrict__ pb2, int valid, int root, int agent,
-                                            uint32_t ex1, uint32_t ex2)
+                                            uint32_t ex1, uint32_t ex2, uint32_t stage)
 {
     const Thr t;
     const int A = d.A, cc = t.part * 16;
@@ -510,9 +548,35 @@ __device__ __noinline__ void epi_policy_out(const Desc &d, uint32_t trow, const 
         s += o.x; sbeta += o.y;
     }
     if (t.part == 0 && valid && d.greedy) d.greedy[(size_t)root * d.N + agent] = am;
-    const int ta = (d.cur < 0) ? agent : (agent == d.cur ? 0 : -1);
+    const float invs = 1.f / s, invb = 1.f / sbeta;
+    if (d.cur < 0) {
+        // joint mode: the rows of a quadrant are consecutive (root, agent) pairs, i.e. ONE contiguous block of probs / beta in
+        // global memory: stage the quadrant's block in shared memory and copy it out with coalesced stores (a row-per-thread
+        // store touches 32 sectors per instruction: ~13 k cycles per tile at 27m)
+        const uint32_t st = stage + (uint32_t)t.quad * (32u * 48u * 4u);
+        const int rpw = 32 / d.N;
+        const int first_root = root - t.lane / d.N;                       // (valid lanes) root of lane 0 of this quadrant
+        const int q_root0 = __shfl_sync(0xffffffffu, first_root, 0);
+        const int nroots = max(0, min(rpw, d.B - q_root0));
+        const int nflt = nroots * d.N * A;
+        const size_t gbase = (size_t)q_root0 * d.N * A;
+        const int idx = t.part * 32 + t.lane;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (cc + i < A) sts1f(st + (uint32_t)(t.lane * A + cc + i) * 4u, pass == 0 ? v[i] * invs : (unit_tau ? v[i] : __powf(v[i], d.inv_tau)) * invb);
+            }
+            named_bar_sync(1 + t.quad, 128);
+            float *dst = (pass == 0 ? d.probs : d.beta) + gbase;
+            for (int k = idx; k < nflt; k += 128) dst[k] = lds1v(st + (uint32_t)k * 4u);
+            named_bar_sync(1 + t.quad, 128);
+        }
+        return;
+    }
+    const int ta = (agent == d.cur ? 0 : -1);
     if (active && valid && ta >= 0) {
-        const float invs = 1.f / s, invb = 1.f / sbeta;
         float *po = d.probs + ((size_t)root * d.Nt + ta) * A, *bo = d.beta + ((size_t)root * d.Nt + ta) * A;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -549,32 +613,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
     const uint32_t tmem = tmem_base_s;
 
     if (warp == NEPI / 32) {
-        // ================================ weight producer: stage-major, each stage's pieces once per tile ==================
+        // ================================ weight producer: every piece once, in stage order (both tiles use it) ============
         if ((tid & 31) == 0) {
             int pc = 0;
 #pragma unroll 1
-            for (int i = 0; i < NOPS;) {
-                int j = i;
-                while (!kOps[j].last) ++j;
+            for (int o = 0; o < NOPS; ++o) {
+                const int mat = kOps[o].mat;
+                uint32_t n, k;
+                mat_dims(mat, d.NAP, n, k);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(d.wpk) + d.chunk_off[mat];
 #pragma unroll 1
-                for (int tt = 0; tt < 2; ++tt)
-#pragma unroll 1
-                    for (int o = i; o <= j; ++o) {
-                        const int mat = kOps[o].mat;
-                        uint32_t n, k;
-                        mat_dims(mat, d.NAP, n, k);
-                        const uint8_t *src = reinterpret_cast<const uint8_t *>(d.wpk) + d.chunk_off[mat];
-#pragma unroll 1
-                        for (uint32_t k0 = 0; k0 < k; k0 += 64, ++pc) {
-                            const uint32_t kk = min(64u, k - k0), bytes = n * kk * 2u;
-                            const int s = pc % NSLOT;
-                            if (pc >= NSLOT) mbar_wait_backoff(&bar_empty[s], ((pc / NSLOT) - 1) & 1);
-                            mbar_expect_tx(&bar_full[s], bytes);
-                            bulk_g2s(sW + (size_t)s * SLOT_BYTES, src, bytes, &bar_full[s]);
-                            src += bytes;
-                        }
-                    }
-                i = j + 1;
+                for (uint32_t k0 = 0; k0 < k; k0 += 64, ++pc) {
+                    const uint32_t kk = min(64u, k - k0), bytes = n * kk * 2u;
+                    const int s = pc % NSLOT;
+                    if (pc >= NSLOT) mbar_wait_backoff(&bar_empty[s], ((pc / NSLOT) - 1) & 1);
+                    mbar_expect_tx(&bar_full[s], bytes);
+                    bulk_g2s(sW + (size_t)s * SLOT_BYTES, src, bytes, &bar_full[s]);
+                    src += bytes;
+                }
             }
         }
     } else if (warp == NEPI / 32 + 1) {
@@ -587,10 +643,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
             int j = i;
             while (!kOps[j].last) ++j;
 #pragma unroll 1
+            const int pc0 = pc;      // a stage's pieces (<= NSLOT) stay resident for both tiles: tile 0 waits for them, tile 1 releases them
+#pragma unroll 1
             for (int tt = 0; tt < 2; ++tt) {
                 named_bar_sync(5, NEPI + 32);                    // tile tt's operands for this stage are published
                 tc_fence_after();
                 if (issuer) {
+                    pc = pc0;
 #pragma unroll 1
                     for (int o = i; o <= j; ++o) {
                         const Op op = kOps[o];
@@ -602,10 +661,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
                         for (uint32_t k0 = 0; k0 < k; k0 += 64, ++pc) {
                             const uint32_t kk = min(64u, k - k0);
                             const int s = pc % NSLOT;
-                            mbar_wait(&bar_full[s], (pc / NSLOT) & 1);
-                            tc_fence_after();
+                            if (tt == 0) {
+                                mbar_wait(&bar_full[s], (pc / NSLOT) & 1);
+                                tc_fence_after();
+                            }
                             issue_gemm(dst, a_addr, k, k0, aW + (uint32_t)s * SLOT_BYTES, kk, 0, kk, n, op.acc != 0 || k0 != 0);
-                            mma_commit(&bar_empty[s]);           // the slot is free once these MMAs have read it
+                            if (tt == 1) mma_commit(&bar_empty[s]);   // the slot is free once both tiles' MMAs have read it
                         }
                     }
                     mma_commit(&bar_mma[tt]);
@@ -684,7 +745,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
 #pragma unroll 1
         for (int tt = 0; tt < 2; ++tt) {
             TILE_VARS
-            fused::gather_hidden(hrow, valid, aT);
+            gather_hidden(hrow, valid, aT);
             PUBLISH();
         }
         // ---- attention_stack[0..1]: x0 = relu(W_in [h | onehot] + b) + positional table ------------------------------------
@@ -698,7 +759,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
             STAGE(epi_ln(trow, lv + 384, lv + 512, lv + 640, nullptr, aX, 0, aX, aRed));              // norm1(x + out_proj)
             STAGE(epi_bias(trow, lv + 768, 1, aT));                                                   // relu(linear1)
             STAGE(epi_ln(trow, lv + 896, lv + 1024, lv + 1152, nullptr, aX, 0, aX, aRed);             // norm2(x + linear2)
-                  if (l == 2) fused::gather_hidden(hrow, valid, aT));                                 // h (bf16) back for fc_dynamic
+                  if (l == 2) gather_hidden(hrow, valid, aT));                                 // h (bf16) back for fc_dynamic
         }
         // ---- fc_dynamic: Linear-LN-ReLU, Linear-LN-ReLU, Linear; residual (model.py:262-268) --------------------------------
         const float *dv = P + d.o_dyn;
@@ -726,7 +787,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
         for (int tt = 0; tt < 2; ++tt) {
             TILE_VARS
             WAIT_MMA();
-            epi_policy_out(d, trow, pv + 96, valid, root, agent, aRed, aScr);
+            epi_policy_out(d, trow, pv + 96, valid, root, agent, aRed, aRed + 4096, aScr);
             named_bar_sync(1 + t.quad, 128);        // (the other tile's call reuses the exchange buffers)
             TS();
         }

@@ -210,8 +210,8 @@ class FusedParams:
         bp2 = torch.cat([g(p + "fc_policy.3.bias"), torch.zeros(KA - A, device=dev)])
         put("pol", g(p + "fc_policy.0.bias"), g(p + "fc_policy.1.weight"), g(p + "fc_policy.1.bias"), bp2)
         vecf = torch.cat(vec)
-        if vecf.numel() % 4:
-            vecf = torch.cat([vecf, torch.zeros(4 - vecf.numel() % 4, device=dev)])
+        if vecf.numel() % 8:      # (a multiple of 4 for the bulk copy; of 8 so that the tables behind it are 32-byte aligned)
+            vecf = torch.cat([vecf, torch.zeros(8 - vecf.numel() % 8, device=dev)])
         vecf = vecf.contiguous()
         assert all(o % 4 == 0 for o in self.off.values())
         self.off_oh = [vecf.numel() + i * A * H for i in range(3)]
