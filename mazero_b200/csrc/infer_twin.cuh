@@ -130,6 +130,39 @@ __device__ __forceinline__ void add_xres(float (&v)[NV], uint32_t tile, int row,
         }
     }
 }
+// v += b with Blackwell's packed fp32 adds
+template <int NV>
+__device__ __forceinline__ void add_regs(float (&v)[NV], const float (&b)[NV])
+{
+#pragma unroll
+    for (int i = 0; i < NV; i += 2) {
+        const float2 r = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b[i], b[i + 1]));
+        v[i] = r.x; v[i + 1] = r.y;
+    }
+}
+template <int NV>
+__device__ __forceinline__ void load_gvec(float (&b)[NV], const float *__restrict__ p)
+{
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p + i));
+        b[i] = t.x; b[i + 1] = t.y; b[i + 2] = t.z; b[i + 3] = t.w;
+    }
+}
+// v = (v - mean) * rstd * g + b as a = rstd*g; v = v*a + (b - mean*a), packed
+template <int NV>
+__device__ __forceinline__ void ln_affine_p(float (&v)[NV], float mean, float rstd, const float *__restrict__ pg, const float *__restrict__ pb)
+{
+    const float2 r2 = make_float2(rstd, rstd), nm2 = make_float2(-mean, -mean);
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(pg + i)), b = __ldg(reinterpret_cast<const float4 *>(pb + i));
+        const float2 a0 = __fmul2_rn(r2, make_float2(g.x, g.y)), a1 = __fmul2_rn(r2, make_float2(g.z, g.w));
+        const float2 c0 = __ffma2_rn(nm2, a0, make_float2(b.x, b.y)), c1 = __ffma2_rn(nm2, a1, make_float2(b.z, b.w));
+        const float2 y0 = __ffma2_rn(make_float2(v[i], v[i + 1]), a0, c0), y1 = __ffma2_rn(make_float2(v[i + 2], v[i + 3]), a1, c1);
+        v[i] = y0.x; v[i + 1] = y0.y; v[i + 2] = y1.x; v[i + 3] = y1.y;
+    }
+}
 template <int NV>
 __device__ __forceinline__ void ln_affine_g(float (&v)[NV], float mean, float rstd, const float *__restrict__ pg, const float *__restrict__ pb)
 {
@@ -153,6 +186,12 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2f(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 
@@ -180,9 +219,10 @@ __device__ __noinline__ void epi_bias(uint32_t trow, const float *__restrict__ p
 {
     const Thr t;
     const int c = t.part * 32;
-    float v[32];
+    float v[32], b[32];
+    load_gvec(b, pb + c);                      // (issued before the TMEM load: its wait covers the L1 latency)
     tmem_ld32(trow + TM_A0 + c, v);
-    add_gvec(v, pb + c);
+    add_regs(v, b);
     if (relu) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -191,26 +231,31 @@ __device__ __noinline__ void epi_bias(uint32_t trow, const float *__restrict__ p
 }
 // y = LN(acc + b [+ oh] [+ x from res_tile]) * g + be, optional ReLU -> dst tile (bf16)
 __device__ __noinline__ void epi_ln(uint32_t trow, const float *__restrict__ pb, const float *__restrict__ pg, const float *__restrict__ pbe,
-                                    const float *__restrict__ oh, uint32_t res_tile, int relu_after, uint32_t dst_tile, uint32_t aRed)
+                                    const float *__restrict__ oh, uint32_t res_tile, int relu_after, uint32_t dst_tile, uint32_t aRed, int dbg = 0)
 {
     const Thr t;
     const int c = t.part * 32;
-    float v[32];
-    tmem_ld32(trow + TM_A0 + c, v);
-    add_gvec(v, pb + c);
-    if (oh) add_grow(v, oh + c);
-    if (res_tile) add_xres(v, res_tile, t.row, c);
+    float v[32], b[32];
+    load_gvec(b, pb + c);                      // everything that does not depend on the accumulator first
+    if (oh) add_grow(b, oh + c);
+    if (res_tile) add_xres(b, res_tile, t.row, c);
+    if (dbg & 128) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    } else
+        tmem_ld32(trow + TM_A0 + c, v);
+    add_regs(v, b);
     float sum, sq;
     sum_sq(v, sum, sq);
-    row_stats(t, aRed, sum, sq);
+    if (!(dbg & 16)) row_stats(t, aRed, sum, sq);
     const float mean = sum * (1.f / H);
     const float rstd = rsqrtf(fmaxf(sq * (1.f / H) - mean * mean, 0.f) + 1e-5f);
-    ln_affine_g(v, mean, rstd, pg + c, pbe + c);
+    if (!(dbg & 32)) ln_affine_p(v, mean, rstd, pg + c, pbe + c);
     if (relu_after) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    store_cols(dst_tile, t.row, c, H, v);
+    if (!(dbg & 64)) store_cols(dst_tile, t.row, c, H, v);
 }
 
 // Scaled dot-product attention over the agents of a root (attention.py:36-43 -> nn.MultiheadAttention, 8 heads x 16).
@@ -241,9 +286,9 @@ __device__ __noinline__ void epi_attention(uint32_t trow, uint32_t aT, const flo
             tmem_ld16(trow + TM_A0 + hh * HD, q);
             tmem_ld16(trow + TM_A1 + hh * HD, k);
             add_gvec(q, pqk + hh * HD);
-            add_gvec(k, pqk + H + hh * HD);
+            // (no K bias: q . (k + bk) = q . k + a per-query constant, which the softmax over the keys cancels)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) q[i] *= 0.25f;          // 1/sqrt(head_dim): a power of two, exact before the rounding
+            for (int i = 0; i < 16; ++i) q[i] *= 0.25f * 1.4426950408889634f;   // 1/sqrt(head_dim) * log2(e): scores in log2 units
             uint4 a;
             a.x = pack2(q[0], q[1]); a.y = pack2(q[2], q[3]); a.z = pack2(q[4], q[5]); a.w = pack2(q[6], q[7]);
             sts4(qb + mine, a);
@@ -293,7 +338,7 @@ __device__ __noinline__ void epi_attention(uint32_t trow, uint32_t aT, const flo
                 for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const float p = __expf(S[mt][nt][2 * h + e] - mx);
+                        const float p = ex2f(S[mt][nt][2 * h + e] - mx);
                         S[mt][nt][2 * h + e] = p;
                         sum += p;
                     }
@@ -590,7 +635,7 @@ __device__ __noinline__ void epi_policy_out(const Desc &d, uint32_t trow, const 
 __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const __grid_constant__ Desc d)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_mma[2];
+    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_mma[2], bar_ready[2];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -604,6 +649,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
         for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         mbar_init(&bar_mma[0], 1);
         mbar_init(&bar_mma[1], 1);
+        mbar_init(&bar_ready[0], NEPI);
+        mbar_init(&bar_ready[1], NEPI);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -638,6 +685,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
         const bool issuer = (tid & 31) == 0;
         const uint32_t aW = smem_u32(sW);
         int pc = 0;
+        uint32_t rph = 0;
 #pragma unroll 1
         for (int i = 0; i < NOPS;) {
             int j = i;
@@ -646,9 +694,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
             const int pc0 = pc;      // a stage's pieces (<= NSLOT) stay resident for both tiles: tile 0 waits for them, tile 1 releases them
 #pragma unroll 1
             for (int tt = 0; tt < 2; ++tt) {
-                named_bar_sync(5, NEPI + 32);                    // tile tt's operands for this stage are published
-                tc_fence_after();
                 if (issuer) {
+                    mbar_wait(&bar_ready[tt], (rph >> tt) & 1u);   // all 512 epilogue threads have published tile tt's operands
+                    rph ^= 1u << tt;
+                    tc_fence_after();
                     pc = pc0;
 #pragma unroll 1
                     for (int o = i; o <= j; ++o) {
@@ -697,7 +746,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
     const int root = root0 + tt * 4 * rpw;                                \
     const float *hrow = tt ? hrow1 : hrow0;                               \
     const int act = tt ? act1 : act0;                                     \
-    (void)trow, (void)aX, (void)aT, (void)valid, (void)root, (void)hrow, (void)act;
+    const uint32_t aRedT = aRed + (uint32_t)tt * 4096u;                   \
+    (void)trow, (void)aX, (void)aT, (void)valid, (void)root, (void)hrow, (void)act, (void)aRedT;
 #define WAIT_MMA()                                 \
     mbar_wait(&bar_mma[tt], (ph >> tt) & 1u);      \
     ph ^= 1u << tt;                                \
@@ -707,7 +757,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
     TS();                              \
     fence_proxy_async();               \
     tc_fence_before();                 \
-    named_bar_sync(5, NEPI + 32);
+    mbar_arrive(&bar_ready[tt]);
 #define STAGE(body)                            \
     _Pragma("unroll 1") for (int tt = 0; tt < 2; ++tt) { \
         TILE_VARS                              \
@@ -748,6 +798,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
             gather_hidden(hrow, valid, aT);
             PUBLISH();
         }
+
         // ---- attention_stack[0..1]: x0 = relu(W_in [h | onehot] + b) + positional table ------------------------------------
         STAGE(epi_inproj(trow, P + d.o_bin, act >= 0 ? P + d.o_oh_in + act * H : nullptr, P + d.o_pos + agent * H, aX));
         // ---- 3 x post-LN TransformerEncoderLayer over the agent axis (attention.py:36-43) ----------------------------------
@@ -756,33 +807,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
             const float *lv = P + d.o_layer + l * 1280;   // bq bk bv bo g1 be1 b1 b2 g2 be2
             STAGE(epi_bias(trow, lv + 256, 0, aT));                                                   // V
             STAGE(epi_attention(trow, aT, lv, N, aScr));                                              // Q | K -> attention
-            STAGE(epi_ln(trow, lv + 384, lv + 512, lv + 640, nullptr, aX, 0, aX, aRed));              // norm1(x + out_proj)
+            named_bar_sync(5, NEPI);   // the warps' Q / K blocks cover the whole scratch area, row statistics included: nobody may
+                                       // start the next LayerNorm while a slower warp is still in tile B's attention
+            STAGE(epi_ln(trow, lv + 384, lv + 512, lv + 640, nullptr, aX, 0, aX, aRedT, d.dbg_flags));              // norm1(x + out_proj)
             STAGE(epi_bias(trow, lv + 768, 1, aT));                                                   // relu(linear1)
-            STAGE(epi_ln(trow, lv + 896, lv + 1024, lv + 1152, nullptr, aX, 0, aX, aRed);             // norm2(x + linear2)
+            STAGE(epi_ln(trow, lv + 896, lv + 1024, lv + 1152, nullptr, aX, 0, aX, aRedT, d.dbg_flags);             // norm2(x + linear2)
                   if (l == 2) gather_hidden(hrow, valid, aT));                                 // h (bf16) back for fc_dynamic
         }
         // ---- fc_dynamic: Linear-LN-ReLU, Linear-LN-ReLU, Linear; residual (model.py:262-268) --------------------------------
         const float *dv = P + d.o_dyn;
-        STAGE(epi_ln(trow, dv, dv + 128, dv + 256, act >= 0 ? P + d.o_oh_dyn + act * H : nullptr, 0, 1, aT, aRed));
-        STAGE(epi_ln(trow, dv + 384, dv + 512, dv + 640, nullptr, 0, 1, aX, aRed));
+        STAGE(epi_ln(trow, dv, dv + 128, dv + 256, act >= 0 ? P + d.o_oh_dyn + act * H : nullptr, 0, 1, aT, aRedT));
+        STAGE(epi_ln(trow, dv + 384, dv + 512, dv + 640, nullptr, 0, 1, aX, aRedT));
         STAGE(epi_next_hidden(trow, dv + 768, hrow, d.next_hidden + (valid ? (size_t)root * (N * H) + (size_t)agent * H : 0), valid, aT));
         // ---- reward head: GraphNetNN on [next_hidden | onehot] (model.py:270-277) -------------------------------------------
         const float *rv = P + d.o_rg;
-        STAGE(epi_gnn(trow, rv, act >= 0 ? P + d.o_oh_rg + act * H : nullptr, N, root_lane0, 0, aX, aRed, aScr));
+        STAGE(epi_gnn(trow, rv, act >= 0 ? P + d.o_oh_rg + act * H : nullptr, N, root_lane0, 0, aX, aRedT, aScr));
         STAGE({
-            const float r = epi_gnn(trow, rv + 128, nullptr, N, root_lane0, 1, 0, aRed, aScr);
+            const float r = epi_gnn(trow, rv + 128, nullptr, N, root_lane0, 1, 0, aRedT, aScr);
             if (valid && agent == 0 && t.part == 0) d.reward[root] = r;
         });
         // ---- value head: GraphNetNN on next_hidden (model.py:359) -------------------------------------------------------------
         const float *vv = P + d.o_vg;
-        STAGE(epi_gnn(trow, vv, nullptr, N, root_lane0, 0, aX, aRed, aScr));
+        STAGE(epi_gnn(trow, vv, nullptr, N, root_lane0, 0, aX, aRedT, aScr));
         STAGE({
-            const float val = epi_gnn(trow, vv + 128, nullptr, N, root_lane0, 1, 0, aRed, aScr);
+            const float val = epi_gnn(trow, vv + 128, nullptr, N, root_lane0, 1, 0, aRedT, aScr);
             if (valid && agent == 0 && t.part == 0) d.value[root] = val;
         });
         // ---- policy head + the driver's softmax / beta ---------------------------------------------------------------------------
         const float *pv = P + d.o_pol;
-        STAGE(epi_policy_hidden(trow, pv, aX, aRed));
+        STAGE(epi_policy_hidden(trow, pv, aX, aRedT));
 #pragma unroll 1
         for (int tt = 0; tt < 2; ++tt) {
             TILE_VARS
