@@ -518,7 +518,7 @@ def run_ours(args):
             fl = B * FLOP_PER_ROOT.get(args.workload, 0.0)
             from mazero_b200 import fused as _fused
             small = _fused.use_small(B, N)
-            kname = "k_recurrent_inference_small" if small else "k_recurrent_inference"
+            kname = "k_recurrent_inference_small" if small else ("k_recurrent_inference_twin" if _fused.use_twin(B, N) else "k_recurrent_inference")
             roofline = {"bound": "tensor", "kernel": kname, "achieved": fl / (ms_inf * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
                         "frac": fl / (ms_inf * 1e-3) / 1e12 / bf16_peak, "traffic": traffic.get(f"{kname}:{args.workload}:{args.mode}"),
                         "peak_source": peak_src, "algorithmic_flop_per_launch": fl, "launch_ms": ms_inf, "launches_per_search": S,

@@ -44,7 +44,6 @@ using fused::PP;
 using fused::SUP;
 using fused::Thr;
 using fused::pack2;
-using fused::row_stats;
 using fused::store_cols;
 using fused::sum_sq;
 
@@ -195,6 +194,21 @@ __device__ __forceinline__ float ex2f(float x)
 }
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 
+// combine (sum, sumsq) of the four column parts of a row.  Layout [part][row]: the 32 lanes of a warp write / read 256 contiguous
+// bytes (the [row][part] layout of the first kernel is a 4-way bank conflict on every access).
+__device__ __forceinline__ void row_stats_pr(const Thr &t, uint32_t aRed, float &sum, float &sq)
+{
+    sts2f(aRed + (uint32_t)(t.part * 128 + t.row) * 8u, sum, sq);
+    named_bar_sync(1 + t.quad, 128);
+    float S = 0.f, Q = 0.f;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) {
+        const float2 v = lds2f(aRed + (uint32_t)(p * 128 + t.row) * 8u);
+        S += v.x; Q += v.y;
+    }
+    sum = S; sq = Q;
+}
+
 // ---- epilogues (NOT inlined: small code, see infer_fused.cuh) -----------------------------------------------------------------
 // Thread layout as in infer_fused.cuh: 16 warps = 4 TMEM lane quadrants x 4 column parts; row = quad*32 + lane.
 // `trow`: TMEM address of the tile's ACC0 at this warp's lanes; `oh`: this row's column of the one-hot weight block (or NULL).
@@ -247,7 +261,7 @@ __device__ __noinline__ void epi_ln(uint32_t trow, const float *__restrict__ pb,
     add_regs(v, b);
     float sum, sq;
     sum_sq(v, sum, sq);
-    if (!(dbg & 16)) row_stats(t, aRed, sum, sq);
+    if (!(dbg & 16)) row_stats_pr(t, aRed, sum, sq);
     const float mean = sum * (1.f / H);
     const float rstd = rsqrtf(fmaxf(sq * (1.f / H) - mean * mean, 0.f) + 1e-5f);
     if (!(dbg & 32)) ln_affine_p(v, mean, rstd, pg + c, pbe + c);
@@ -454,15 +468,19 @@ __device__ __forceinline__ void root_sum(float (&v)[NV], int lane, int lo, int N
 //            the rows of a root by the part-0 warp (root_sum over 11 values instead of 16 features x 4 parts).  The scalar is
 //            returned by the part-0 thread of every row.
 __device__ __noinline__ float epi_gnn(uint32_t trow, const float *__restrict__ pb, const float *__restrict__ oh, int N, int root_lane0, int head,
-                                      uint32_t tile, uint32_t aRed, uint32_t scratch)
+                                      uint32_t tile, uint32_t aRed, uint32_t scratch, long long *clk = nullptr)
 {
     const Thr t;
+#define SUBTS(i) if (clk) clk[i] = clock64();
+    SUBTS(0)
     const int c = t.part * GP;
     float y[GP], nn[GP];
     tmem_ld16(trow + TM_A0 + c, y);
     add_gvec(y, pb + c);
     if (oh) add_grow(y, oh + c);
+    SUBTS(1)
     root_sum(y, t.lane, root_lane0, N);
+    SUBTS(2)
     tmem_ld16(trow + TM_A0 + GH + c, nn);
     add_gvec(nn, pb + GH + c);
     if (oh) add_grow(nn, oh + GH + c);
@@ -473,7 +491,9 @@ __device__ __noinline__ float epi_gnn(uint32_t trow, const float *__restrict__ p
         sum += y[i];
         sq += y[i] * y[i];
     }
-    row_stats(t, aRed, sum, sq);
+    SUBTS(3)
+    row_stats_pr(t, aRed, sum, sq);
+    SUBTS(4)
     const float mean = sum * (1.f / GH);
     const float rstd = rsqrtf(fmaxf(sq * (1.f / GH) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll
@@ -483,8 +503,12 @@ __device__ __noinline__ float epi_gnn(uint32_t trow, const float *__restrict__ p
         return 0.f;
     }
     const float *pV = pb + 2 * GH, *pVb = pV + SUP * GH;
-    float lg[12];
-    lg[11] = 0.f;
+    // partial-logit exchange area [k = 0..11][part][row] (24 KB): every access of a warp is 128 contiguous bytes
+#define PL(k, part, row) (scratch + (uint32_t)((((k) * PARTS + (part)) * 128 + (row)) * 4))
+    SUBTS(5)
+    named_bar_sync(1 + t.quad, 128);                 // the previous call's partials / results of this quadrant have been consumed
+    SUBTS(6)
+    // (1) partial logits of MY row over MY 16 features
 #pragma unroll
     for (int k = 0; k < SUP; ++k) {
         float a = 0.f;
@@ -493,32 +517,44 @@ __device__ __noinline__ float epi_gnn(uint32_t trow, const float *__restrict__ p
             const float4 w = __ldg(reinterpret_cast<const float4 *>(pV + k * GH + c + i));
             a += w.x * y[i] + w.y * y[i + 1] + w.z * y[i + 2] + w.w * y[i + 3];
         }
-        lg[k] = a;
+        sts1f(PL(k, t.part, t.row), a);
     }
-    const uint32_t mine_out = scratch + (uint32_t)((t.row * PARTS + t.part) * 12) * 4u;
-#pragma unroll
-    for (int k = 0; k < 12; k += 4) sts4(mine_out + 4 * k, make_uint4(__float_as_uint(lg[k]), __float_as_uint(lg[k + 1]), __float_as_uint(lg[k + 2]), __float_as_uint(lg[k + 3])));
+    sts1f(PL(11, t.part, t.row), 0.f);
     named_bar_sync(1 + t.quad, 128);
+    SUBTS(7)
+    // (2) column part p finishes logits 3p .. 3p+2: sum over the four parts of the row, then over the rows of the root; the root's
+    //     first row keeps the result IN PLACE (slot (3p + j, part p, row) is read by nobody else)
+    {
+        float l3[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int q = 0; q < PARTS; ++q) a += lds1v(PL(t.part * 3 + j, q, t.row));
+            l3[j] = a;
+        }
+        SUBTS(8)
+        root_sum(l3, t.lane, root_lane0, N);
+        if (t.lane == root_lane0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) sts1f(PL(t.part * 3 + j, t.part, t.row), l3[j]);
+        }
+    }
+    named_bar_sync(1 + t.quad, 128);
+    SUBTS(9)
+    // (3) mean, bias, softmax . support -> inv_h: the first row of every root, part 0
     float out = 0.f;
-    if (t.part == 0) {                               // warp-uniform
-        const uint32_t rowp = scratch + (uint32_t)(t.row * PARTS * 12) * 4u;
-#pragma unroll
-        for (int p = 1; p < PARTS; ++p)
-#pragma unroll
-            for (int k = 0; k < 12; k += 4) {
-                uint32_t w0, w1, w2, w3;
-                lds4u(rowp + (uint32_t)(p * 12 + k) * 4u, w0, w1, w2, w3);
-                lg[k] += __uint_as_float(w0); lg[k + 1] += __uint_as_float(w1); lg[k + 2] += __uint_as_float(w2); lg[k + 3] += __uint_as_float(w3);
-            }
-        root_sum(lg, t.lane, root_lane0, N);
+    if (t.part == 0 && t.lane == root_lane0) {
         const float invn = 1.f / (float)N;
         float l11[SUP];
 #pragma unroll
-        for (int k = 0; k < SUP; ++k) l11[k] = lg[k] * invn + __ldg(pVb + k);
+        for (int k = 0; k < SUP; ++k) l11[k] = lds1v(PL(k, k / 3, t.row)) * invn + __ldg(pVb + k);
         out = fused::support_to_scalar(l11);
     }
-    named_bar_sync(1 + t.quad, 128);                 // the partials are consumed: the other tile's call may overwrite them
-    return out;
+    SUBTS(10)
+#undef SUBTS
+#undef PL
+    return out;      // (valid on the first row of a root, part 0; no trailing barrier: the next writer of the partials synchronises first)
 }
 
 // policy hidden: p1 = relu(LN(acc + b) * g + be) over 32 columns -> operand tile (K = 32)
@@ -532,7 +568,7 @@ __device__ __noinline__ void epi_policy_hidden(uint32_t trow, const float *__res
     float sum = 0.f, sq = 0.f;
 #pragma unroll
     for (int i = 0; i < PP; ++i) { sum += p[i]; sq += p[i] * p[i]; }
-    row_stats(t, aRed, sum, sq);
+    row_stats_pr(t, aRed, sum, sq);
     const float mean = sum * (1.f / PH);
     const float rstd = rsqrtf(fmaxf(sq * (1.f / PH) - mean * mean, 0.f) + 1e-5f);
     ln_affine_g(p, mean, rstd, pp + PH + c, pp + 2 * PH + c);
@@ -542,16 +578,20 @@ __device__ __noinline__ void epi_policy_hidden(uint32_t trow, const float *__res
 }
 
 // policy logits -> softmax -> probs, beta = probs^(1/tau) renormalised (mcts_sampled.py:158-161), greedy action.
-// Column part p owns logits [16p, 16p + 16) of its row (parts beyond the padded action count idle); row maximum / argmax and the
-// two sums are combined across the parts of a row through shared memory (ex1, ex2: 4 KB each).
+// Column part p owns logits [16p, 16p + 16) of its row (parts beyond the padded action count idle).  Every part reduces its own
+// columns (local maximum m_p, argmax, sum of exp(v - m_p), sum of exp((v - m_p)/tau)); ONE exchange through shared memory (ex: 8 KB)
+// combines them: M = max m_p, s = sum s_p exp(m_p - M).
 __device__ __noinline__ void epi_policy_out(const Desc &d, uint32_t trow, const float *__restrict__ pb2, int valid, int root, int agent,
-                                            uint32_t ex1, uint32_t ex2, uint32_t stage)
+                                            uint32_t ex, uint32_t stage, long long *clk = nullptr)
 {
     const Thr t;
+#define SUBTS(i) if (clk) clk[i] = clock64();
+    SUBTS(0)
     const int A = d.A, cc = t.part * 16;
     const bool active = cc < d.NAP;                  // warp-uniform (tcgen05.ld is warp-collective)
+    const bool unit_tau = (d.inv_tau == 1.0f);
     float v[16];
-    float m = -INFINITY;
+    float m = -INFINITY, s = 0.f, sbeta = 0.f;
     int am = 0;
     if (active) {
         tmem_ld16(trow + TM_A0 + cc, v);
@@ -564,18 +604,6 @@ __device__ __noinline__ void epi_policy_out(const Desc &d, uint32_t trow, const 
             for (int i = 0; i < 16; ++i)
                 if (cc + i < A) d.logits_out[((size_t)root * d.N + agent) * A + cc + i] = v[i];
         }
-    }
-    sts2f(ex1 + (uint32_t)(t.row * PARTS + t.part) * 8u, m, __int_as_float(am));
-    named_bar_sync(1 + t.quad, 128);
-    m = -INFINITY;
-#pragma unroll
-    for (int p = 0; p < PARTS; ++p) {                // first maximum in column order, as torch.argmax
-        const float2 o = lds2f(ex1 + (uint32_t)(t.row * PARTS + p) * 8u);
-        if (o.x > m) { m = o.x; am = __float_as_int(o.y); }
-    }
-    const bool unit_tau = (d.inv_tau == 1.0f);
-    float s = 0.f, sbeta = 0.f;
-    if (active) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float e = (cc + i < A) ? __expf(v[i] - m) : 0.f;
@@ -584,41 +612,62 @@ __device__ __noinline__ void epi_policy_out(const Desc &d, uint32_t trow, const 
             sbeta += unit_tau ? e : ((cc + i < A) ? __powf(e, d.inv_tau) : 0.f);   // (e/s)^t = e^t / s^t
         }
     }
-    sts2f(ex2 + (uint32_t)(t.row * PARTS + t.part) * 8u, s, sbeta);
+    SUBTS(1)
+    sts4(ex + (uint32_t)(t.part * 128 + t.row) * 16u, make_uint4(__float_as_uint(m), (uint32_t)am, __float_as_uint(s), __float_as_uint(sbeta)));
     named_bar_sync(1 + t.quad, 128);
+    SUBTS(2)
+    float M = -INFINITY, mp[PARTS], sp[PARTS], bp[PARTS];
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) {                // first maximum in column order, as torch.argmax
+        uint32_t w0, w1, w2, w3;
+        lds4u(ex + (uint32_t)(p * 128 + t.row) * 16u, w0, w1, w2, w3);
+        mp[p] = __uint_as_float(w0); sp[p] = __uint_as_float(w2); bp[p] = __uint_as_float(w3);
+        if (mp[p] > M) { M = mp[p]; am = (int)w1; }
+    }
     s = 0.f; sbeta = 0.f;
 #pragma unroll
     for (int p = 0; p < PARTS; ++p) {
-        const float2 o = lds2f(ex2 + (uint32_t)(t.row * PARTS + p) * 8u);
-        s += o.x; sbeta += o.y;
+        const float f = __expf(mp[p] - M);           // (idle parts: exp(-inf) = 0)
+        s += sp[p] * f;
+        sbeta += bp[p] * (unit_tau ? f : __powf(f, d.inv_tau));
     }
+    const float mine = __expf(m - M);                // my columns were taken relative to my part's maximum
     if (t.part == 0 && valid && d.greedy) d.greedy[(size_t)root * d.N + agent] = am;
-    const float invs = 1.f / s, invb = 1.f / sbeta;
+    const float invs = mine / s, invb = (unit_tau ? mine : __powf(mine, d.inv_tau)) / sbeta;
+    SUBTS(3)
     if (d.cur < 0) {
         // joint mode: the rows of a quadrant are consecutive (root, agent) pairs, i.e. ONE contiguous block of probs / beta in
         // global memory: stage the quadrant's block in shared memory and copy it out with coalesced stores (a row-per-thread
-        // store touches 32 sectors per instruction: ~13 k cycles per tile at 27m)
+        // store touches 32 sectors per instruction: ~13 k cycles per tile at 27m).  tau = 1: beta == probs, one pass.
         const uint32_t st = stage + (uint32_t)t.quad * (32u * 48u * 4u);
         const int rpw = 32 / d.N;
-        const int first_root = root - t.lane / d.N;                       // (valid lanes) root of lane 0 of this quadrant
-        const int q_root0 = __shfl_sync(0xffffffffu, first_root, 0);
+        const int q_root0 = __shfl_sync(0xffffffffu, root, 0);          // lane 0 holds the quadrant's first root
         const int nroots = max(0, min(rpw, d.B - q_root0));
         const int nflt = nroots * d.N * A;
         const size_t gbase = (size_t)q_root0 * d.N * A;
         const int idx = t.part * 32 + t.lane;
+        const int npass = unit_tau ? 1 : 2;
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = 0; pass < npass; ++pass) {
+            if (pass) named_bar_sync(1 + t.quad, 128);                   // pass 0 has been copied out
             if (active) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    if (cc + i < A) sts1f(st + (uint32_t)(t.lane * A + cc + i) * 4u, pass == 0 ? v[i] * invs : (unit_tau ? v[i] : __powf(v[i], d.inv_tau)) * invb);
+                    if (cc + i < A) sts1f(st + (uint32_t)(t.lane * A + cc + i) * 4u, pass == 0 ? v[i] * invs : __powf(v[i], d.inv_tau) * invb);
             }
+            SUBTS(4)
             named_bar_sync(1 + t.quad, 128);
-            float *dst = (pass == 0 ? d.probs : d.beta) + gbase;
-            for (int k = idx; k < nflt; k += 128) dst[k] = lds1v(st + (uint32_t)k * 4u);
-            named_bar_sync(1 + t.quad, 128);
+            SUBTS(5)
+            float *dst = (pass == 0 ? d.probs : d.beta) + gbase, *dst2 = d.beta + gbase;
+            for (int k = idx; k < nflt; k += 128) {
+                const float x = lds1v(st + (uint32_t)k * 4u);
+                dst[k] = x;
+                if (unit_tau) dst2[k] = x;
+            }
         }
-        return;
+        SUBTS(6)
+#undef SUBTS
+        return;     // (the next writer of the staging area passes this function's first barrier again, after every warp's copy loop)
     }
     const int ta = (agent == d.cur ? 0 : -1);
     if (active && valid && ta >= 0) {
@@ -627,7 +676,7 @@ __device__ __noinline__ void epi_policy_out(const Desc &d, uint32_t trow, const 
         for (int i = 0; i < 16; ++i)
             if (cc + i < A) {
                 po[cc + i] = v[i] * invs;
-                bo[cc + i] = (unit_tau ? v[i] : __powf(v[i], d.inv_tau)) * invb;
+                bo[cc + i] = (unit_tau ? v[i] * invs : __powf(v[i], d.inv_tau) * invb);
             }
     }
 }
@@ -690,7 +739,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
         for (int i = 0; i < NOPS;) {
             int j = i;
             while (!kOps[j].last) ++j;
-#pragma unroll 1
             const int pc0 = pc;      // a stage's pieces (<= NSLOT) stay resident for both tiles: tile 0 waits for them, tile 1 releases them
 #pragma unroll 1
             for (int tt = 0; tt < 2; ++tt) {
@@ -731,12 +779,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
         const int rpw = 32 / N;
         const int rl = t.lane / N, agent = t.lane - rl * N;
         const int root_lane0 = (rl < rpw) ? rl * N : 0;
-        const int root0 = ((blockIdx.x * 2) * 4 + t.quad) * rpw + rl;          // tile tt: + tt * 4 * rpw
-        const int valid0 = (rl < rpw) && (root0 < d.B), valid1 = (rl < rpw) && (root0 + 4 * rpw < d.B);
         const uint32_t trow0 = tmem + ((uint32_t)(t.quad * 32) << 16);
         uint32_t ph = 0;
         int ts_n = 0;
-        const bool ts_on = d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0;
 #define TS() \
     if (ts_on && ts_n < 256) d.dbg_clock[ts_n++] = clock64();
 #define TILE_VARS                                                         \
@@ -768,6 +813,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
 
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        const int root0 = ((blockIdx.x * 2) * 4 + t.quad) * rpw + rl;          // tile tt: + tt * 4 * rpw
+        const int valid0 = (rl < rpw) && (root0 < d.B), valid1 = (rl < rpw) && (root0 + 4 * rpw < d.B);
+        const bool ts_on = d.dbg_clock != nullptr && blockIdx.x == 0 && tid == 0;
         // ---- per tile: the parent's hidden-state row and my agent's action ------------------------------------------------
         const float *hrow0 = d.pool, *hrow1 = d.pool;
         int act0 = -1, act1 = -1;
@@ -823,7 +871,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
         const float *rv = P + d.o_rg;
         STAGE(epi_gnn(trow, rv, act >= 0 ? P + d.o_oh_rg + act * H : nullptr, N, root_lane0, 0, aX, aRedT, aScr));
         STAGE({
-            const float r = epi_gnn(trow, rv + 128, nullptr, N, root_lane0, 1, 0, aRedT, aScr);
+            const float r = epi_gnn(trow, rv + 128, nullptr, N, root_lane0, 1, 0, aRedT, aScr, ts_on ? d.dbg_clock + 128 + 16 * tt : nullptr);
             if (valid && agent == 0 && t.part == 0) d.reward[root] = r;
         });
         // ---- value head: GraphNetNN on next_hidden (model.py:359) -------------------------------------------------------------
@@ -836,12 +884,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
         // ---- policy head + the driver's softmax / beta ---------------------------------------------------------------------------
         const float *pv = P + d.o_pol;
         STAGE(epi_policy_hidden(trow, pv, aX, aRedT));
+        named_bar_sync(5, NEPI);   // the policy exchange buffer covers both tiles' row-statistics buffers: every warp must have left
+                                   // tile B's LayerNorm before the first one writes it
 #pragma unroll 1
         for (int tt = 0; tt < 2; ++tt) {
             TILE_VARS
             WAIT_MMA();
-            epi_policy_out(d, trow, pv + 96, valid, root, agent, aRed, aRed + 4096, aScr);
-            named_bar_sync(1 + t.quad, 128);        // (the other tile's call reuses the exchange buffers)
+            epi_policy_out(d, trow, pv + 96, valid, root, agent, aRed, aScr, ts_on ? d.dbg_clock + 160 + 16 * tt : nullptr);
             TS();
         }
 #undef STAGE

@@ -238,7 +238,7 @@ class FusedParams:
         dsc.factor, dsc.greedy_pool, dsc.roots_per_tile = ptr(factor), ptr(greedy_pool), int(roots_per_tile)
         import os as _os
         dsc.dbg_flags = int(_os.environ.get('MAZ_DBG_FLAGS', '0'))
-        twin = (not small) and (use_twin() if twin is None else bool(twin))
+        twin = (not small) and (use_twin(B, self.N) if twin is None else bool(twin))
         dsc.wpk, dsc.vec, dsc.vec_floats = (self.wpk_h if small else self.wpk).data_ptr(), self.vec.data_ptr(), self.vec.numel()
         co, cb = (self.chunk_off_h, self.chunk_bytes_h) if small else (self.chunk_off, self.chunk_bytes)
         if twin:
@@ -268,9 +268,18 @@ FusedParams.weights_desc = _weights_desc
 SMALL_MAX_TILES = int(os.environ.get("MAZ_INFER_SMALL_MAX_TILES", "222"))   # 1.5 waves of 148 SMs (measured cross-over, profiles/prof_infer_cmp.py)
 
 
-def use_twin():
-    """Large-batch kernel generation: two tiles in flight per CTA (csrc/infer_twin.cuh) unless MAZ_INFER_TC=v1."""
-    return os.environ.get("MAZ_INFER_TC", "twin") != "v1"
+def use_twin(B=None, N=None):
+    """Which large-batch kernel: two tiles in flight per CTA (csrc/infer_twin.cuh) or the first generation, one tile per CTA
+    (csrc/infer_fused.cuh).  MAZ_INFER_TC=twin|v1 forces one.  Measured per launch (profiles/prof_infer.py): a pair of tiles takes
+    ~158 us whatever the team size, one first-generation tile 93 us (N = 3..5), 118 us (N = 10), 170 us (N = 27): with at most one
+    tile per SM the first generation is the shorter chain for small teams; everywhere else the pairs win."""
+    mode = os.environ.get("MAZ_INFER_TC", "auto")
+    if mode in ("twin", "v1"):
+        return mode == "twin"
+    if B is None or N is None:
+        return True
+    tiles = -(-int(B) // (4 * (32 // int(N))))
+    return tiles > 148 or int(N) >= 8
 
 
 def use_small(B, N):

@@ -38,5 +38,13 @@ if os.environ.get("STAGE_CLOCKS"):
     inf.recurrent_fused(B, pool, idx, act, pool[1], rew, val, probs, beta, dbg_clock=dbg)
     torch.cuda.synchronize()
     t = dbg.cpu().numpy()
+    sub = t[128:]
+    t = t[:128]
     t = t[t > 0]
     print("stage clocks (cycles since first):", (t - t[0]).tolist())
+    if sub.any():      # sub-phase clocks of one epilogue (two tiles x 16 entries), when the kernel was built with them
+        for k in range(0, len(sub), 16):
+            u = sub[k:k + 16]
+            u = u[u > 0]
+            if len(u):
+                print("sub-phase cycles:", (u[1:] - u[:-1]).tolist())

@@ -97,11 +97,13 @@ def test_full_size_conservation_independence_determinism(built_lib, name):
 
     Bs = max(32 // N, 1) * 13 + 1           # not a multiple of any tile size
     os.environ["MAZ_INFER_KERNEL"] = "small" if fused.use_small(B, N) else "tcgen05"
+    os.environ["MAZ_INFER_TC"] = "twin" if fused.use_twin(B, N) else "v1"       # (and the same tcgen05 kernel generation)
     try:
         sub_args = _setup(name, B=Bs)
         sub, _ = _run(*sub_args)
     finally:
         del os.environ["MAZ_INFER_KERNEL"]
+        del os.environ["MAZ_INFER_TC"]
     for k in full:
         assert np.array_equal(full[k][:Bs], sub[k]), f"independence: {k}"
     del plan
