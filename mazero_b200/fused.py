@@ -272,14 +272,14 @@ def use_twin(B=None, N=None):
     """Which large-batch kernel: two tiles in flight per CTA (csrc/infer_twin.cuh) or the first generation, one tile per CTA
     (csrc/infer_fused.cuh).  MAZ_INFER_TC=twin|v1 forces one.  Measured per launch (profiles/prof_infer.py): a pair of tiles takes
     ~158 us whatever the team size, one first-generation tile 93 us (N = 3..5), 118 us (N = 10), 170 us (N = 27): with at most one
-    tile per SM the first generation is the shorter chain for small teams; everywhere else the pairs win."""
+    tile per SM the first generation is the shorter chain except for the largest teams; everywhere else the pairs win."""
     mode = os.environ.get("MAZ_INFER_TC", "auto")
     if mode in ("twin", "v1"):
         return mode == "twin"
     if B is None or N is None:
         return True
     tiles = -(-int(B) // (4 * (32 // int(N))))
-    return tiles > 148 or int(N) >= 8
+    return tiles > 148 or int(N) >= 20
 
 
 def use_small(B, N):
