@@ -31,7 +31,8 @@ def test_umma_gemm_stage(built_lib, n, k):
 
 @pytest.mark.parametrize("kernel", ["twin", "tcgen05", "small"])
 @pytest.mark.parametrize("N,A,B", [(3, 9, 100), (5, 11, 70), (10, 18, 33), (27, 36, 9), (1, 5, 130), (2, 3, 16), (2, 40, 20),
-                                   (30, 17, 5), (3, 9, 1), (27, 36, 1300)])   # 1300 x 27: 325 tiles, the persistent twin kernel loops
+                                   (30, 17, 5), (3, 9, 1), (27, 36, 1300),    # 1300 x 27: 325 tiles = more than one wave of tile pairs
+                                   (8, 12, 40), (16, 6, 10)])                # teams that fill a 32-row warp exactly
 def test_fused_recurrent_inference_matches_fp32_reference(built_lib, N, A, B, kernel):
     """bf16 tensor-core kernels (tcgen05 128-row tiles; small-batch 32-row tiles on warp-level MMAs) vs the plain fp32 torch
     forward (same weights).  Tolerance: bf16 operand
