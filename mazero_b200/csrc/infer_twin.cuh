@@ -13,7 +13,8 @@
 //     the other tile's epilogue.
 //   * TMEM: 256 columns per tile (ACC0 | ACC1).  The fp32 residual stream of the first kernel (128 more columns per tile) is
 //     gone: x lives only as the bf16 operand tile and `x + f(x)` is added in the epilogue from that tile.
-//   * q|k|v is two stages: V first (drained as bf16 into the tile that will receive the attention output), then Q|K.
+//   * q|k|v is two stages of four heads each ([Q | K] in ACC0, V in ACC1): no stage needs more than 192 columns, and each has a
+//     full attention epilogue behind it (a separate V stage had a 1 k-cycle epilogue that could not cover the next MMA group).
 //   * Attention over the agents of a root on warp-level tensor-core MMAs (mma.sync.m16n8k16, bf16): a warp holds 32 token
 //     rows (whole roots) and two heads; S = Q K^T (32 x 32 x 16) with a block-diagonal root mask, softmax on the accumulator
 //     fragments, O = P V (32 x 16 x 32).  The tcgen05 operand layout is made of 8 x 16-byte core matrices, which is exactly
@@ -53,30 +54,31 @@ constexpr uint32_t TILE_BYTES = 128 * 128 * 2;     // one bf16 operand tile
 constexpr uint32_t SCRATCH_BYTES = 32768;          // attention Q/K blocks (16 warps x 2 KB) | graph-head partials 24 KB + row statistics 4 KB
 constexpr uint32_t RED_OFF = 24576;
 constexpr uint32_t TM_TILE = 256, TM_A0 = 0, TM_A1 = 128;
-constexpr int NOPS = 29;                           // weight matrices = MMA groups per tile
+constexpr int NOPS = 32;                           // weight matrices = MMA groups per tile
 constexpr int NSTAGE = 25;
 
 __host__ __device__ inline size_t smem_bytes() { return 4 * (size_t)TILE_BYTES + SCRATCH_BYTES + NSLOT * (size_t)SLOT_BYTES + 1024; }
 
 // One MMA group: D[tile ACC `dst`] (+)= A[tile `asrc`: 0 = sX, 1 = sT] * W[mat]^T; `last` closes a stage.
 struct Op { unsigned char mat, asrc, dst, acc, last; };
-#define MAZ_TW_LAYER(b) {b, 0, 0, 0, 1}, {b + 1, 0, 0, 0, 0}, {b + 2, 0, 1, 0, 1}, {b + 3, 1, 0, 0, 1}, {b + 4, 0, 0, 0, 1}, {b + 5, 1, 0, 0, 1}
+#define MAZ_TW_LAYER(b) {b, 0, 0, 0, 0}, {b + 1, 0, 1, 0, 1}, {b + 2, 0, 0, 0, 0}, {b + 3, 0, 1, 0, 1}, {b + 4, 1, 0, 0, 1}, {b + 5, 0, 0, 0, 1}, {b + 6, 1, 0, 0, 1}
 __constant__ Op kOps[NOPS] = {
     {0, 1, 0, 0, 1},                                       // in-proj on h
-    MAZ_TW_LAYER(1), MAZ_TW_LAYER(7), MAZ_TW_LAYER(13),    // per layer: V | Q, K | out-proj | linear1 | linear2
-    {19, 1, 0, 0, 0}, {20, 0, 0, 1, 1},                    // fc_dynamic.0 on [h | . | attention output]
-    {21, 1, 0, 0, 1}, {22, 0, 0, 0, 1},                    // fc_dynamic.3, fc_dynamic.6
-    {23, 1, 0, 0, 1}, {24, 0, 0, 0, 1},                    // reward graph net layer 1 (on h'), layer 2
-    {25, 1, 0, 0, 1}, {26, 0, 0, 0, 1},                    // value graph net
-    {27, 1, 0, 0, 1}, {28, 0, 0, 0, 1},                    // fc_policy.0, fc_policy.3
+    MAZ_TW_LAYER(1), MAZ_TW_LAYER(8), MAZ_TW_LAYER(15),    // per layer: [Q|K heads 0-3, V heads 0-3] | [Q|K, V heads 4-7] | out-proj | linear1 | linear2
+    {22, 1, 0, 0, 0}, {23, 0, 0, 1, 1},                    // fc_dynamic.0 on [h | . | attention output]
+    {24, 1, 0, 0, 1}, {25, 0, 0, 0, 1},                    // fc_dynamic.3, fc_dynamic.6
+    {26, 1, 0, 0, 1}, {27, 0, 0, 0, 1},                    // reward graph net layer 1 (on h'), layer 2
+    {28, 1, 0, 0, 1}, {29, 0, 0, 0, 1},                    // value graph net
+    {30, 1, 0, 0, 1}, {31, 0, 0, 0, 1},                    // fc_policy.0, fc_policy.3
 };
 #undef MAZ_TW_LAYER
 __device__ __forceinline__ void mat_dims(int m, int NAP, uint32_t &n, uint32_t &k)
 {
     n = 128; k = 128;
-    if (m == 24 || m == 26) k = GH;
-    else if (m == 27) n = PH;
-    else if (m == 28) { n = (uint32_t)NAP; k = PH; }
+    if (m >= 1 && m <= 21 && ((m - 1) % 7 == 1 || (m - 1) % 7 == 3)) n = 64;      // V of four heads
+    else if (m == 27 || m == 29) k = GH;
+    else if (m == 30) n = PH;
+    else if (m == 31) { n = (uint32_t)NAP; k = PH; }
 }
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------------
@@ -273,13 +275,14 @@ __device__ __noinline__ void epi_ln(uint32_t trow, const float *__restrict__ pb,
 }
 
 // Scaled dot-product attention over the agents of a root (attention.py:36-43 -> nn.MultiheadAttention, 8 heads x 16).
-// ACC0 = x Wq^T, ACC1 = x Wk^T (this stage), aT = bf16(x Wv^T + bv) (previous stage); the output replaces V in aT.
-// A warp (quad, part) owns token rows quad*32 .. +31 and heads 2*part, 2*part + 1; per head:
+// A layer's q|k|v projection is two stages of four heads each (`half`): ACC0 = [Q | K] of heads 4*half .. +3 (64 + 64 columns),
+// ACC1 = V of the same heads (64 columns).  A warp (quad, part) owns token rows quad*32 .. +31 and head 4*half + part:
+//   V (+ bias) of the 32 rows -> bf16 into the head's 16 columns of aT (the tile that receives the attention output);
 //   Q (scaled by 1/sqrt(16), + bias) and K (+ bias) of the 32 rows -> two 32 x 16 bf16 blocks in the warp's scratch (core-matrix
 //   layout), S[32 x 32] = Q K^T on 8 MMAs, keys of other roots masked, row softmax on the fragments (a row's 32 scores sit in
 //   the 4 lanes of a quad), P as bf16 A fragments, O[32 x 16] = P V on 8 MMAs with V fragments by ldmatrix.trans from aT.
 // Rows beyond the last whole root of the warp form a pseudo-root of their own (finite garbage, never stored anywhere).
-__device__ __noinline__ void epi_attention(uint32_t trow, uint32_t aT, const float *__restrict__ pqk, int N, uint32_t scratch)
+__device__ __noinline__ void epi_attention(uint32_t trow, uint32_t aT, const float *__restrict__ pqk, int N, uint32_t scratch, int half)
 {
     const Thr t;
     const int l = t.lane, m = l >> 3;
@@ -293,12 +296,22 @@ __device__ __noinline__ void epi_attention(uint32_t trow, uint32_t aT, const flo
             const int r = mt * 16 + (l >> 2) + 8 * h;
             rs[mt][h] = (r / N) * N;
         }
-#pragma unroll 1
-    for (int hh = t.part * 2; hh < t.part * 2 + 2; ++hh) {
+    {
+        const int hh = half * 4 + t.part;
         {
             float q[16], k[16];
-            tmem_ld16(trow + TM_A0 + hh * HD, q);
-            tmem_ld16(trow + TM_A1 + hh * HD, k);
+            {
+                float v[16];
+                tmem_ld16(trow + TM_A1 + t.part * HD, v);
+                add_gvec(v, pqk + 2 * H + hh * HD);
+                uint4 a;
+                a.x = pack2(v[0], v[1]); a.y = pack2(v[2], v[3]); a.z = pack2(v[4], v[5]); a.w = pack2(v[6], v[7]);
+                sts4(aT + operand_chunk_off(t.row, hh * 2, H, 128), a);
+                a.x = pack2(v[8], v[9]); a.y = pack2(v[10], v[11]); a.z = pack2(v[12], v[13]); a.w = pack2(v[14], v[15]);
+                sts4(aT + operand_chunk_off(t.row, hh * 2 + 1, H, 128), a);
+            }
+            tmem_ld16(trow + TM_A0 + t.part * HD, q);
+            tmem_ld16(trow + TM_A0 + 64 + t.part * HD, k);
             add_gvec(q, pqk + hh * HD);
             // (no K bias: q . (k + bk) = q . k + a per-query constant, which the softmax over the keys cancels)
 #pragma unroll
@@ -391,7 +404,6 @@ __device__ __noinline__ void epi_attention(uint32_t trow, uint32_t aT, const flo
                     sts32(aT + operand_chunk_off(row, hh * 2 + n2, H, 128) + (uint32_t)(l & 3) * 4u,
                           pack2(O[mt][n2][2 * h] * inv[mt][h], O[mt][n2][2 * h + 1] * inv[mt][h]));
                 }
-        __syncwarp();                                            // Q / K blocks are free for the next head
     }
 }
 
@@ -853,8 +865,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
             const float *lv = P + d.o_layer + l * 1280;   // bq bk bv bo g1 be1 b1 b2 g2 be2
-            STAGE(epi_bias(trow, lv + 256, 0, aT));                                                   // V
-            STAGE(epi_attention(trow, aT, lv, N, aScr));                                              // Q | K -> attention
+            STAGE(epi_attention(trow, aT, lv, N, aScr, 0));                                           // heads 0-3: Q | K | V -> attention
+            STAGE(epi_attention(trow, aT, lv, N, aScr, 1));                                           // heads 4-7
             named_bar_sync(5, NEPI);   // the warps' Q / K blocks cover the whole scratch area, row statistics included: nobody may
                                        // start the next LayerNorm while a slower warp is still in tile B's attention
             STAGE(epi_ln(trow, lv + 384, lv + 512, lv + 640, nullptr, aX, 0, aX, aRedT, d.dbg_flags));              // norm1(x + out_proj)

@@ -161,14 +161,17 @@ class FusedParams:
         self.chunk_off = offs
         self.chunk_bytes = [t.numel() * 2 for t in packed]
 
-        # two-tiles-in-flight kernel (csrc/infer_twin.cuh): 29 matrices in the order of its stage table (per layer V, Q, K,
-        # out-proj, linear1, linear2; no one-hot blocks), each stored as K-halves (pieces of <= 64 input features, <= 16 KB)
+        # two-tiles-in-flight kernel (csrc/infer_twin.cuh): 32 matrices in the order of its stage table (per layer [Q|K] and V of
+        # heads 0-3, of heads 4-7, out-proj, linear1, linear2; no one-hot blocks), each stored as K-halves (<= 64 input features, <= 16 KB)
         tw = [c[0]]
         for l in range(3):
             b = 2 + 6 * l
-            tw += [c[b + 2], c[b], c[b + 1], c[b + 3], c[b + 4], c[b + 5]]
+            wq, wk, wv = c[b], c[b + 1], c[b + 2]
+            for h in (0, 1):                  # four heads per stage: [Q rows | K rows] stacked (128 x 128), V rows (64 x 128)
+                tw += [torch.cat([wq[64 * h:64 * h + 64], wk[64 * h:64 * h + 64]], 0), wv[64 * h:64 * h + 64]]
+            tw += [c[b + 3], c[b + 4], c[b + 5]]
         tw += [c[20], c[22], c[23], c[24], c[25], c[27], c[28], c[29], c[30], c[31]]
-        assert len(tw) == 29
+        assert len(tw) == NCHUNK
         tp = []
         for m in tw:
             m = m.contiguous()
@@ -178,7 +181,7 @@ class FusedParams:
             offs_t.append(o)
             o += t.numel() * 2
         wpk_t = torch.cat(tp)
-        self.chunk_off_t, self.chunk_bytes_t = offs_t + [0] * (NCHUNK - 29), [t.numel() * 2 for t in tp] + [0] * (NCHUNK - 29)
+        self.chunk_off_t, self.chunk_bytes_t = offs_t, [t.numel() * 2 for t in tp]
         if getattr(self, "wpk_t", None) is None:
             self.wpk_t = wpk_t
         else:

@@ -3,7 +3,7 @@ kernel (csrc/infer_twin.cuh): per stage and tile, epilogue cycles (accumulator r
 (publish of the previous epilogue -> this tile's accumulator ready).    python profiles/decode_twin_clocks.py LOGFILE"""
 import sys
 
-NAMES = ["inproj"] + sum([[f"L{l}.V", f"L{l}.attn", f"L{l}.ln1", f"L{l}.relu", f"L{l}.ln2"] for l in range(3)], []) + \
+NAMES = ["inproj"] + sum([[f"L{l}.att0", f"L{l}.att1", f"L{l}.ln1", f"L{l}.relu", f"L{l}.ln2"] for l in range(3)], []) + \
         ["dyn0", "dyn1", "nexth", "rL1", "rhead", "vL1", "vhead", "polh", "polout"]
 
 for line in open(sys.argv[1]):

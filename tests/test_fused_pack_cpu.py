@@ -1,5 +1,5 @@
 """CPU: host-side weight packing of the two-tiles-in-flight inference kernel (mazero_b200/fused.py, csrc/infer_twin.cuh):
-29 matrices in the order of the kernel's stage table, stored as K-halves in the tcgen05 core-matrix layout, one-hot weight
+32 matrices in the order of the kernel's stage table, stored as K-halves in the tcgen05 core-matrix layout, one-hot weight
 blocks as fp32 [A][128] tables of the bf16-rounded weights behind the parameter vector; descriptor fields; kernel selection."""
 import torch
 
@@ -22,7 +22,10 @@ def _expected_matrices(sd, A, KA):
     for l in range(3):
         e = f"{d}attention_stack.2.encoder.layers.{l}."
         qkv = g(e + "self_attn.in_proj_weight")
-        out += [qkv[2 * H:3 * H], qkv[0:H], qkv[H:2 * H], g(e + "self_attn.out_proj.weight"), g(e + "linear1.weight"), g(e + "linear2.weight")]
+        q, k, v = qkv[0:H], qkv[H:2 * H], qkv[2 * H:3 * H]
+        for h in (0, 1):      # four heads per stage: [Q rows | K rows] stacked, then the V rows
+            out += [torch.cat([q[64 * h:64 * h + 64], k[64 * h:64 * h + 64]], 0), v[64 * h:64 * h + 64]]
+        out += [g(e + "self_attn.out_proj.weight"), g(e + "linear1.weight"), g(e + "linear2.weight")]
     wd1 = g(d + "fc_dynamic.0.weight")
     out += [wd1[:, :H], wd1[:, H + A:], g(d + "fc_dynamic.3.weight"), g(d + "fc_dynamic.6.weight")]
     r, v = d + "reward_predictor.", p + "value_predictor."
@@ -41,7 +44,7 @@ def test_twin_packing_roundtrip(built_lib):
     sd = random_state_dict(N, A, seed=3)
     fp = fused.FusedParams(sd, N, A, "cpu")
     mats, (w_in, wd1, wr1) = _expected_matrices(sd, A, fp.KA)
-    assert len(mats) == 29 and fp.chunk_bytes_t[29:] == [0] * (fused.NCHUNK - 29)
+    assert len(mats) == fused.NCHUNK == len(fp.chunk_bytes_t)
     raw = fp.wpk_t
     for i, m in enumerate(mats):
         rows, k = m.shape
