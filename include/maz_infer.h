@@ -54,7 +54,8 @@ typedef struct maz_infer_desc {
     /* maz_infer_recurrent only: which large-batch kernel `wpk` / `vec` / the chunk table are packed for.
      * 0: one tile per CTA (csrc/infer_fused.cuh; 32 chunks, `vec` copied to shared memory).
      * 1: two tiles in flight per CTA (csrc/infer_twin.cuh; 32 matrices stored as K-halves in the order of its stage table,
-     *    `vec` read from global memory and followed by the three one-hot weight blocks W_a^T as fp32 [A][128] tables). */
+     *    `vec` read from global memory and followed by the three one-hot weight blocks W_a^T as bf16 [A][128] tables,
+     *    i.e. [A][64] 32-bit words). */
     int tc_layout;
     int o_oh_in, o_oh_dyn, o_oh_rg;   /* tc_layout 1: float offsets into vec of the one-hot blocks of attention_stack.0 /
                                          fc_dynamic.0 / reward_predictor layer 1 (gc | nn stacked) */

@@ -21,7 +21,7 @@
 //     what ldmatrix reads: V fragments come straight from the operand tile (ldmatrix.trans).  16 MMAs per head and warp
 //     whatever the team size (the scalar loop was ~110 instructions per key, head and row).
 //   * The one-hot joint-action operand is gone: `W [h | onehot(a)]` = `W_h h + W_a[:, a]`, the column is added in the epilogue
-//     from an fp32 table (three fewer MMA groups, no one-hot tiles in shared memory).
+//     from a bf16 [A][128] table (three fewer MMA groups, no one-hot tiles in shared memory).
 //   * Weights stream through a 4 x 16 KB ring in K-halves (a 128 x 128 matrix is two pieces), ONCE per CTA: a stage's pieces
 //     (at most 4) serve tile A and then tile B and are released by tcgen05.commit after tile B's MMAs.  Biases / LayerNorm affines / heads are read from global memory (L1-resident):
 //     shared memory holds 4 operand tiles (128 KB) + 32 KB scratch + the ring.
@@ -114,6 +114,22 @@ __device__ __forceinline__ void add_grow(float (&v)[NV], const float *__restrict
         ldg256(p + i, t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i + j] += t[j];
+    }
+}
+// v += NV bf16 values stored as packed pairs in 32-bit words at p (one-hot weight tables: [A][64] words = [A][128] bf16)
+template <int NV>
+__device__ __forceinline__ void add_grow_bf16(float (&v)[NV], const float *__restrict__ p)
+{
+#pragma unroll
+    for (int i = 0; i < NV; i += 16) {
+        float t[8];
+        ldg256(p + i / 2, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t w = __float_as_uint(t[j]);
+            v[i + 2 * j] += __uint_as_float(w << 16);
+            v[i + 2 * j + 1] += __uint_as_float(w & 0xffff0000u);
+        }
     }
 }
 // v += the bf16 row segment [c, c + NV) of `row` in a K = 128 operand tile (the residual stream)
@@ -224,7 +240,7 @@ __device__ __noinline__ void epi_inproj(uint32_t trow, const float *__restrict__
     float v[32];
     tmem_ld32(trow + TM_A0 + c, v);
     add_gvec(v, pb + c);
-    if (oh) add_grow(v, oh + c);
+    if (oh) add_grow_bf16(v, oh + c / 2);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     add_grow(v, pos + c);
@@ -253,7 +269,7 @@ __device__ __noinline__ void epi_ln(uint32_t trow, const float *__restrict__ pb,
     const int c = t.part * 32;
     float v[32], b[32];
     load_gvec(b, pb + c);                      // everything that does not depend on the accumulator first
-    if (oh) add_grow(b, oh + c);
+    if (oh) add_grow_bf16(b, oh + c / 2);
     if (res_tile) add_xres(b, res_tile, t.row, c);
     if (dbg & 128) {
 #pragma unroll
@@ -489,13 +505,13 @@ __device__ __noinline__ float epi_gnn(uint32_t trow, const float *__restrict__ p
     float y[GP], nn[GP];
     tmem_ld16(trow + TM_A0 + c, y);
     add_gvec(y, pb + c);
-    if (oh) add_grow(y, oh + c);
+    if (oh) add_grow_bf16(y, oh + c / 2);
     SUBTS(1)
     root_sum(y, t.lane, root_lane0, N);
     SUBTS(2)
     tmem_ld16(trow + TM_A0 + GH + c, nn);
     add_gvec(nn, pb + GH + c);
-    if (oh) add_grow(nn, oh + GH + c);
+    if (oh) add_grow_bf16(nn, oh + (GH + c) / 2);
     float sum = 0.f, sq = 0.f;
 #pragma unroll
     for (int i = 0; i < GP; ++i) {
@@ -860,7 +876,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
         }
 
         // ---- attention_stack[0..1]: x0 = relu(W_in [h | onehot] + b) + positional table ------------------------------------
-        STAGE(epi_inproj(trow, P + d.o_bin, act >= 0 ? P + d.o_oh_in + act * H : nullptr, P + d.o_pos + agent * H, aX));
+        STAGE(epi_inproj(trow, P + d.o_bin, act >= 0 ? P + d.o_oh_in + act * (H / 2) : nullptr, P + d.o_pos + agent * H, aX));
         // ---- 3 x post-LN TransformerEncoderLayer over the agent axis (attention.py:36-43) ----------------------------------
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
@@ -876,12 +892,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_recurrent_inference_twin(const 
         }
         // ---- fc_dynamic: Linear-LN-ReLU, Linear-LN-ReLU, Linear; residual (model.py:262-268) --------------------------------
         const float *dv = P + d.o_dyn;
-        STAGE(epi_ln(trow, dv, dv + 128, dv + 256, act >= 0 ? P + d.o_oh_dyn + act * H : nullptr, 0, 1, aT, aRedT));
+        STAGE(epi_ln(trow, dv, dv + 128, dv + 256, act >= 0 ? P + d.o_oh_dyn + act * (H / 2) : nullptr, 0, 1, aT, aRedT));
         STAGE(epi_ln(trow, dv + 384, dv + 512, dv + 640, nullptr, 0, 1, aX, aRedT));
         STAGE(epi_next_hidden(trow, dv + 768, hrow, d.next_hidden + (valid ? (size_t)root * (N * H) + (size_t)agent * H : 0), valid, aT));
         // ---- reward head: GraphNetNN on [next_hidden | onehot] (model.py:270-277) -------------------------------------------
         const float *rv = P + d.o_rg;
-        STAGE(epi_gnn(trow, rv, act >= 0 ? P + d.o_oh_rg + act * H : nullptr, N, root_lane0, 0, aX, aRedT, aScr));
+        STAGE(epi_gnn(trow, rv, act >= 0 ? P + d.o_oh_rg + act * (H / 2) : nullptr, N, root_lane0, 0, aX, aRedT, aScr));
         STAGE({
             const float r = epi_gnn(trow, rv + 128, nullptr, N, root_lane0, 1, 0, aRedT, aScr, ts_on ? d.dbg_clock + 128 + 16 * tt : nullptr);
             if (valid && agent == 0 && t.part == 0) d.reward[root] = r;

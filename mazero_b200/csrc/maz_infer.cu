@@ -104,7 +104,7 @@ extern "C" int maz_infer_recurrent(const maz_infer_desc *d, void *stream)
     if (d->vec_floats <= 0 || d->vec_floats % 4) return set_last_error(1, "maz_infer_recurrent: vec_floats must be a positive multiple of 4");
     const bool tw = d->tc_layout == 1;
     if (d->tc_layout != 0 && !tw) return set_last_error(1, "maz_infer_recurrent: unknown tc_layout");
-    if (tw && (d->o_oh_in <= 0 || d->o_oh_dyn <= 0 || d->o_oh_rg <= 0 || d->o_oh_rg + d->A * 128 > d->vec_floats))
+    if (tw && (d->o_oh_in <= 0 || d->o_oh_dyn <= 0 || d->o_oh_rg <= 0 || d->o_oh_rg + d->A * 64 > d->vec_floats))
         return set_last_error(1, "maz_infer_recurrent: tc_layout 1 needs the one-hot weight tables behind vec");
     const size_t dyn = tw ? twin::smem_bytes() : fused::smem_bytes(d->KA, d->vec_floats);
     if (dyn > 227 * 1024) return set_last_error(3, "maz_infer_recurrent: parameters do not fit in shared memory");

@@ -186,8 +186,8 @@ class FusedParams:
             self.wpk_t = wpk_t
         else:
             self.wpk_t.copy_(wpk_t)
-        # the one-hot blocks as fp32 [A][128] tables of the bf16-rounded weights (what the one-hot MMA would have added)
-        oh = [w[:, H:H + A].to(torch.bfloat16).to(torch.float32).t().contiguous() for w in (w_in, wd1, wr1)]
+        # the one-hot blocks as bf16 [A][128] tables (what the one-hot MMA would have added), stored as [A][64] 32-bit words
+        oh = [w[:, H:H + A].t().contiguous().to(torch.bfloat16).view(torch.float32) for w in (w_in, wd1, wr1)]
 
         vec, self.off = [], {}
 
@@ -217,7 +217,7 @@ class FusedParams:
             vecf = torch.cat([vecf, torch.zeros(8 - vecf.numel() % 8, device=dev)])
         vecf = vecf.contiguous()
         assert all(o % 4 == 0 for o in self.off.values())
-        self.off_oh = [vecf.numel() + i * A * H for i in range(3)]
+        self.off_oh = [vecf.numel() + i * A * (H // 2) for i in range(3)]
         vec_t = torch.cat([vecf] + [t.reshape(-1) for t in oh]).contiguous()
         if self.wpk is None:
             self.wpk, self.vec, self.vec_t = wpk, vecf, vec_t

@@ -58,13 +58,13 @@ def test_twin_packing_roundtrip(built_lib):
             got[:, k0:k0 + kk] = _unpack_operand(raw[off:off + rows * kk], rows, kk)
             off += rows * kk
         assert torch.equal(got, m.to(torch.bfloat16)), f"matrix {i}"
-    # one-hot blocks: table[a][col] = bf16(W[col, H + a]) as fp32, 32-byte aligned behind the fp32 parameter vector
+    # one-hot blocks: table[a][col] = bf16(W[col, H + a]), 32-byte aligned behind the fp32 parameter vector
     assert fp.vec.numel() % 8 == 0 and torch.equal(fp.vec_t[:fp.vec.numel()], fp.vec)
     for off, w in zip(fp.off_oh, (w_in, wd1, wr1)):
         assert off % 8 == 0
-        tab = fp.vec_t[off:off + A * H].view(A, H)
-        assert torch.equal(tab, w[:, H:H + A].to(torch.bfloat16).float().t())
-    assert fp.vec_t.numel() == fp.off_oh[2] + A * H
+        tab = fp.vec_t[off:off + A * H // 2].contiguous().view(torch.bfloat16).view(A, H)     # [A][64] words = [A][128] bf16
+        assert torch.equal(tab, w[:, H:H + A].to(torch.bfloat16).t())
+    assert fp.vec_t.numel() == fp.off_oh[2] + A * H // 2
 
 
 def test_twin_descriptor_and_selection(built_lib, monkeypatch):
