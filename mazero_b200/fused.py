@@ -273,16 +273,21 @@ SMALL_MAX_TILES = int(os.environ.get("MAZ_INFER_SMALL_MAX_TILES", "222"))   # 1.
 
 def use_twin(B=None, N=None):
     """Which large-batch kernel: two tiles in flight per CTA (csrc/infer_twin.cuh) or the first generation, one tile per CTA
-    (csrc/infer_fused.cuh).  MAZ_INFER_TC=twin|v1 forces one.  Measured per launch (profiles/prof_infer.py): a pair of tiles takes
-    ~158 us whatever the team size, one first-generation tile 93 us (N = 3..5), 118 us (N = 10), 170 us (N = 27): with at most one
-    tile per SM the first generation is the shorter chain except for the largest teams; everywhere else the pairs win."""
+    (csrc/infer_fused.cuh).  MAZ_INFER_TC=twin|v1 forces one.  Cost model from profiles/r02_infer_cmp.log (per launch, B200): a wave
+    of tile PAIRS takes ~141-146 us whatever the team size, a wave of single first-generation tiles 88 us (N = 3), 96 (N = 5),
+    117 (N = 10), 166 (N = 27) ~ 80 + 3.2 N; the kernel with the shorter sum of waves on 148 SMs is taken (e.g. 3m-shaped 16 384
+    roots: 3 x 88 us of single tiles beat 2 x 141 us of pairs; 2s3z 4096 roots: one wave of pairs beats two of single tiles)."""
     mode = os.environ.get("MAZ_INFER_TC", "auto")
     if mode in ("twin", "v1"):
         return mode == "twin"
     if B is None or N is None:
         return True
+    sms = 148
     tiles = -(-int(B) // (4 * (32 // int(N))))
-    return tiles > 148 or int(N) >= 20
+    pairs = (tiles + 1) // 2
+    t_pairs = -(-pairs // sms) * (141.0 + 0.2 * int(N))
+    t_tiles = -(-tiles // sms) * (80.0 + 3.2 * int(N))
+    return t_pairs < t_tiles
 
 
 def use_small(B, N):

@@ -591,6 +591,13 @@ class SampledMCTS(object):
 
                 h = int(getattr(model, "hidden_state_size_per_agent", getattr(model, "hidden", 128)))
                 mode = "bf16" if fused.supported(sd, int(model.num_agents), int(model.action_space_size), h) else "fp32"
+                if mode == "fp32":      # not silent: the fused kernels cover the reference SMAC architecture only (fused.supported)
+                    import warnings
+
+                    warnings.warn("mazero_b200: this network is not the reference SMAC architecture (hidden 128, 3 x 8-head encoder "
+                                  "layers, support 11, <= 30 agents, <= 48 actions): the search runs its forward as plain fp32 torch "
+                                  "ops on the device (parity mode), not through the fused tensor-core kernels", RuntimeWarning,
+                                  stacklevel=3)
             inf = SmacInference.from_model(model, device=dev, mode=mode)
         else:
             inf.refresh(sd)

@@ -1,4 +1,5 @@
-"""Fused inference: tcgen05 kernel (128-row tiles) vs small-batch kernel (32-row tiles, warp-level MMAs), per-launch time by batch."""
+"""Fused inference, per-launch time by batch: tcgen05 kernels (128-row tiles; "twin" = two tiles in flight per CTA, "tcgen05" = first
+generation, one tile per CTA) vs the small-batch kernel (32-row tiles, warp-level MMAs)."""
 import os
 import sys
 
@@ -19,7 +20,7 @@ for name, B in shapes:
     r, v = torch.empty(B, device=dev), torch.empty(B, device=dev)
     p, b = torch.empty(B, N, A, device=dev), torch.empty(B, N, A, device=dev)
     res = {}
-    for kern in ("tcgen05", "small"):
+    for kern in ("twin", "tcgen05", "small"):
         for _ in range(5):
             inf.recurrent_fused(B, pool, idx, act, pool[1], r, v, p, b, kernel=kern)
         torch.cuda.synchronize()
@@ -32,4 +33,4 @@ for name, B in shapes:
         torch.cuda.synchronize()
         res[kern] = e0.elapsed_time(e1) / 50 * 1e3
     rpt = 32 // N
-    print(f"{name:5s} B={B:6d} tiles tcgen05={-(-B // (4 * rpt)):5d} small={-(-B // rpt):5d}   tcgen05 {res['tcgen05']:8.1f} us   small {res['small']:8.1f} us", flush=True)
+    print(f"{name:5s} B={B:6d} tiles tcgen05={-(-B // (4 * rpt)):5d} small={-(-B // rpt):5d}   twin {res['twin']:8.1f} us   tcgen05 (v1) {res['tcgen05']:8.1f} us   small {res['small']:8.1f} us", flush=True)

@@ -77,10 +77,11 @@ def test_twin_descriptor_and_selection(built_lib, monkeypatch):
     assert d0.tc_layout == 0 and d0.vec_floats == fp.vec.numel() and d0.wpk == fp.wpk.data_ptr()
     ds = fp.desc(8192, None, None, None, None, None, None, None, None, small=True, twin=True)     # the small-batch layout ignores it
     assert ds.tc_layout == 0 and ds.wpk == fp.wpk_h.data_ptr()
-    # selection: more than one 128-row tile per SM, or a team of >= 20 agents -> pairs of tiles; env override
+    # selection by the wave cost model (pairs: ~141 us per wave; single tiles: ~80 + 3.2 N us per wave); env override
     monkeypatch.delenv("MAZ_INFER_TC", raising=False)
     assert fused.use_twin(8192, 10) and not fused.use_twin(1024, 10) and fused.use_twin(64, 27)
     assert fused.use_twin(4096, 5) and not fused.use_twin(2048, 3)
+    assert fused.use_twin(8192, 3) and not fused.use_twin(16384, 3)          # 2 x 88 us vs 141 us; 3 x 88 us vs 2 x 141 us
     monkeypatch.setenv("MAZ_INFER_TC", "v1")
     assert not fused.use_twin(8192, 10)
     monkeypatch.setenv("MAZ_INFER_TC", "twin")
