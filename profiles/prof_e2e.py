@@ -28,6 +28,9 @@ for _ in range(20):
     mcts.batch_search(inf, out, None, None, N, None, dev, add_noise=True)
 pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(30)
+from mazero_b200 import hostrng as _h
+print("speculation:", _h.STATS)
 
 # ---- wall-clock split of one search (host side) ------------------------------------------------------------------
 import time
