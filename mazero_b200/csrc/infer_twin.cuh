@@ -3,7 +3,7 @@
 // Same computation as infer_fused.cuh (config/smac/model.py:562-574 = dynamics :251-282 with attention.py:27-43, prediction
 // :335-373, GraphNetNN :136-174; inverse support transform core/config.py:430-442,463-499; the driver's softmax / beta
 // mcts_sampled.py:158-161), restructured around what bounded the first kernel at 2s3z / MMM2 / 27m batch sizes
-// (profiles/r01_ncu_summary.md): one tile per CTA walks 25 dependent stages, and in every stage the tensor pipe waits for the
+// (profiles/r01_ncu_summary.md, profiles/r02_ncu_summary.md): one tile per CTA walks 25 dependent stages, and in every stage the tensor pipe waits for the
 // epilogue warps and the epilogue warps for the tensor pipe (MMA + hand-offs were ~1/3 of a tile's time); and the attention
 // over the agent axis was scalar code whose cost grew with the team size (27m: about half of the tile time).
 //
@@ -16,15 +16,20 @@
 //   * q|k|v is two stages of four heads each ([Q | K] in ACC0, V in ACC1): no stage needs more than 192 columns, and each has a
 //     full attention epilogue behind it (a separate V stage had a 1 k-cycle epilogue that could not cover the next MMA group).
 //   * Attention over the agents of a root on warp-level tensor-core MMAs (mma.sync.m16n8k16, bf16): a warp holds 32 token
-//     rows (whole roots) and two heads; S = Q K^T (32 x 32 x 16) with a block-diagonal root mask, softmax on the accumulator
+//     rows (whole roots) and one head per stage; S = Q K^T (32 x 32 x 16) with a block-diagonal root mask, softmax on the accumulator
 //     fragments, O = P V (32 x 16 x 32).  The tcgen05 operand layout is made of 8 x 16-byte core matrices, which is exactly
 //     what ldmatrix reads: V fragments come straight from the operand tile (ldmatrix.trans).  16 MMAs per head and warp
 //     whatever the team size (the scalar loop was ~110 instructions per key, head and row).
 //   * The one-hot joint-action operand is gone: `W [h | onehot(a)]` = `W_h h + W_a[:, a]`, the column is added in the epilogue
 //     from a bf16 [A][128] table (three fewer MMA groups, no one-hot tiles in shared memory).
 //   * Weights stream through a 4 x 16 KB ring in K-halves (a 128 x 128 matrix is two pieces), ONCE per CTA: a stage's pieces
-//     (at most 4) serve tile A and then tile B and are released by tcgen05.commit after tile B's MMAs.  Biases / LayerNorm affines / heads are read from global memory (L1-resident):
-//     shared memory holds 4 operand tiles (128 KB) + 32 KB scratch + the ring.
+//     (at most 4) serve tile A and then tile B and are released by tcgen05.commit after tile B's MMAs.  Biases / LayerNorm
+//     affines / heads are read from global memory (L1-resident): shared memory holds 4 operand tiles (128 KB) + 32 KB scratch
+//     + the ring.
+//   * Hand-off: the 512 epilogue threads publish a tile's operands by arriving on an mbarrier the MMA thread waits on; they
+//     never wait for each other per stage.  Shared exchange areas are double-buffered by tile or quadrant-local behind
+//     quadrant barriers; two CTA-wide barriers per pass fence the places where a warp-local area covers another quadrant's
+//     buffer (DESIGN.md section 5d lists the hazards).
 #pragma once
 #include "infer_fused.cuh"
 
@@ -55,7 +60,6 @@ constexpr uint32_t SCRATCH_BYTES = 32768;          // attention Q/K blocks (16 w
 constexpr uint32_t RED_OFF = 24576;
 constexpr uint32_t TM_TILE = 256, TM_A0 = 0, TM_A1 = 128;
 constexpr int NOPS = 32;                           // weight matrices = MMA groups per tile
-constexpr int NSTAGE = 25;
 
 __host__ __device__ inline size_t smem_bytes() { return 4 * (size_t)TILE_BYTES + SCRATCH_BYTES + NSLOT * (size_t)SLOT_BYTES + 1024; }
 
