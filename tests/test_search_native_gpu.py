@@ -201,3 +201,25 @@ def test_plan_cache_respects_its_byte_budget(built_lib):
     finally:
         ms.PLAN_CACHE_BYTES = old
         ms.clear_caches()
+
+
+@pytest.mark.parametrize("gen", ["twin", "v1"])
+@pytest.mark.parametrize("cur", [None, 0, 2])
+def test_graph_loop_on_the_tcgen05_kernels_equals_the_legacy_loop(built_lib, monkeypatch, gen, cur):
+    """The library-built graph with the 128-row tcgen05 kernels (both generations; forced: at this batch size the small-batch
+    kernel would be picked) against the round-1 Python loop on the same kernel: in the sequential-agent mode the former assembles
+    the joint action INSIDE the inference kernel (factor | tree action | greedy of the parent, mcts_sampled.py:116-147), the latter
+    in Python -- bit-identical SearchOutputs prove the in-kernel assembly of either generation."""
+    from mazero_b200.mcts_sampled import SampledMCTS, clear_caches
+
+    monkeypatch.setenv("MAZ_INFER_KERNEL", "tcgen05")
+    monkeypatch.setenv("MAZ_INFER_TC", gen)
+    N, A, B, K, S = 3, 9, 100, 10, 20
+    inf, out0, factor, legal = _problem(N, A, B, seed=3)
+    cfg = MockConfig(N, A, S, K)
+    outs = {}
+    for strat in ("graph", "legacy"):
+        mcts = SampledMCTS(cfg, np.random.RandomState(1), search_strategy=strat)
+        outs[strat] = mcts.batch_search(inf, out0, cur, factor, N, legal, DEV, add_noise=True)
+    clear_caches()
+    _equal(outs["graph"], outs["legacy"], f"graph vs legacy ({gen}): ")
