@@ -83,6 +83,14 @@ def test_fused_recurrent_inference_matches_fp32_reference(built_lib, N, A, B, ke
     assert torch.allclose(p1[:, 0], probs[:, cur], atol=1e-6)
     bt = probs[:, cur] ** 0.5
     assert torch.allclose(b1[:, 0], bt / bt.sum(-1, keepdim=True), atol=1e-4)
+    # joint mode with a sampling temperature: every agent's beta = probs^(1/tau) renormalised (mcts_sampled.py:160)
+    p2 = torch.full((B, N, A), float("nan"), device=dev)
+    b2 = torch.full((B, N, A), float("nan"), device=dev)
+    fus.recurrent_fused(B, pool, idx, act, nxt, rew, val, p2, b2, None, None, inv_tau=0.5, kernel=kernel)
+    torch.cuda.synchronize()
+    assert torch.allclose(p2, probs, atol=1e-6)
+    bt = probs ** 0.5
+    assert torch.allclose(b2, bt / bt.sum(-1, keepdim=True), atol=1e-4)
 
 
 @pytest.mark.parametrize("N,A,B", [(27, 36, 300), (5, 11, 1000), (10, 18, 500)])
